@@ -1,0 +1,270 @@
+/*
+ * wrt.h — C ABI of the B200 render back end ("weekend ray tracer", wrt).
+ *
+ * This is the drop-in boundary for the reference's render hot path.  The reference
+ * (j-helland/zig-weekend-raytracer, Zig) has no plugin/FFI seam on that path; the seam is
+ *
+ *     pub fn render(self: *const Renderer, camera: *const Camera, entity: *const IEntity,
+ *                   framebuffer: *Framebuffer) !void                      (src/render.zig:29)
+ *
+ * reached from Scene.draw (src/scene.zig:57-61) and main (src/main.zig:96).  A Zig maintainer
+ * replaces the body of Renderer.render with: walk the IEntity / IMaterial / ITexture tree into
+ * the POD arrays below (wrt_scene), then wrt_upload_scene + wrt_render.  The binding follows the
+ * only FFI idiom the reference has (extern fn + opaque pointer + int status, as in
+ * libs/zstbi/src/zstbi.zig:454-560); see INTEGRATION.md for the Zig stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative WRT_E_* code on failure; the text of the
+ *     last failure is available from wrt_last_error().  No exceptions or callbacks cross the ABI.
+ *   - all arrays are caller-owned and copied during the call (ownership is one-directional).
+ *   - all reals are IEEE-754 binary64 (math.zig:40 `pub const Real = f64`), vectors are xyz triples.
+ *   - indices are uint32_t; WRT_NONE means "null pointer / optional absent".
+ *   - a wrt_ctx is bound to ONE CUDA device and is thread-compatible (one caller at a time).
+ *   - there is no CPU fallback: every entry point that renders fails with WRT_E_CUDA if the device
+ *     or the kernels are unavailable.
+ */
+#ifndef WRT_H
+#define WRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WRT_ABI_VERSION 1u
+#define WRT_NONE 0xFFFFFFFFu
+
+/* status codes */
+enum {
+    WRT_OK = 0,
+    WRT_E_INVALID = -1,  /* bad argument / malformed scene */
+    WRT_E_CUDA = -2,     /* CUDA runtime error (text in wrt_last_error) */
+    WRT_E_NOMEM = -3,    /* host or device allocation failed */
+    WRT_E_STATE = -4,    /* call order violated (e.g. render before upload) */
+    WRT_E_LIMIT = -5     /* scene exceeds a compiled-in limit (transform nesting, ...) */
+};
+
+/* IEntity variants (src/entity.zig:17-24) */
+enum {
+    WRT_ENT_SPHERE = 0,
+    WRT_ENT_QUAD = 1,
+    WRT_ENT_COLLECTION = 2,
+    WRT_ENT_BVH_NODE = 3,
+    WRT_ENT_TRANSLATE = 4,
+    WRT_ENT_ROTATE_Y = 5
+};
+
+/* IMaterial variants (src/material.zig:25-32) */
+enum {
+    WRT_MAT_LAMBERTIAN = 0,
+    WRT_MAT_ISOTROPIC = 1,
+    WRT_MAT_METAL = 2,
+    WRT_MAT_DIELECTRIC = 3,
+    WRT_MAT_DIFFUSE_EMISSIVE = 4
+};
+
+/* ITexture variants (src/texture.zig:11-16) */
+enum { WRT_TEX_SOLID = 0, WRT_TEX_CHECKER = 1, WRT_TEX_IMAGE = 2 };
+
+/* BVH culling rule used by the device traversal.  Both return the same closest hit
+ * whenever the reference's own boxes are conservative; REFERENCE also reproduces the reference
+ * when they are not. */
+enum {
+    WRT_CULL_TIGHT = 0,     /* 3-axis slab test on boxes recomputed from the primitives (fast path) */
+    WRT_CULL_REFERENCE = 1  /* the reference's test: its cached boxes, x and y only, each axis on its own
+                               (src/math/aabb.zig:80-101 + math.zig:186-190) */
+};
+
+/* One node of the reference's entity tree (src/entity.zig).  `bbox_*` is the cached AABB.min/max the
+ * reference's AABB.hit reads (aabb.zig:23-24,84-85), NOT a recomputed box. */
+typedef struct wrt_entity {
+    uint32_t kind; /* WRT_ENT_* */
+    uint32_t a;    /* sphere/quad: index into spheres[]/quads[]; collection: first slot in children[];
+                      bvh_node: left entity; translate/rotate_y: wrapped entity */
+    uint32_t b;    /* collection: number of children; bvh_node: right entity */
+    uint32_t c;    /* collection: bvh_root entity or WRT_NONE (entity.zig:311) */
+    double p[3];   /* translate: offset (entity.zig:71); rotate_y: {sin_theta, cos_theta, 0} (entity.zig:115-116) */
+    double bbox_min[3];
+    double bbox_max[3];
+} wrt_entity;
+
+/* SphereEntity (src/entity.zig:533-543) */
+typedef struct wrt_sphere {
+    double center[3];
+    double radius;
+    double movement[3]; /* movement_direction; used iff is_moving (entity.zig:590-594,653-656) */
+    uint32_t material;
+    uint32_t is_moving;
+} wrt_sphere;
+
+/* QuadEntity (src/entity.zig:428-442): the derived fields are passed as the reference computed them
+ * in initEntity (entity.zig:444-475) so that device arithmetic starts from identical bits. */
+typedef struct wrt_quad {
+    double start[3];  /* start_point */
+    double u[3];      /* basis.u = axis1 */
+    double v[3];      /* basis.v = axis2 */
+    double w[3];      /* basis.w = n / dot(n,n) */
+    double normal[3]; /* unit normal */
+    double offset;    /* dot(normal, start) */
+    double area;      /* |axis1 x axis2| */
+    uint32_t material;
+    uint32_t _pad;
+} wrt_quad;
+
+/* IMaterial payloads (src/material.zig:79-226) */
+typedef struct wrt_material {
+    uint32_t kind;    /* WRT_MAT_* */
+    uint32_t texture; /* lambertian / isotropic / diffuse_emissive: texture index */
+    double albedo[3]; /* metal */
+    double param;     /* metal: fuzz; dielectric: refraction_index */
+} wrt_material;
+
+/* ITexture payloads (src/texture.zig:33-119) */
+typedef struct wrt_texture {
+    uint32_t kind;  /* WRT_TEX_* */
+    uint32_t even;  /* checker: tex_even index */
+    uint32_t odd;   /* checker: tex_odd index */
+    uint32_t image; /* image: index into images[] */
+    double color[3];  /* solid */
+    double inv_scale; /* checker */
+} wrt_texture;
+
+/* zstbi.Image as consumed by Image.getPixel (src/image.zig:23-36): 8-bit interleaved rows. */
+typedef struct wrt_image {
+    uint32_t width;
+    uint32_t height; /* 0 => the reference's magenta debug colour (texture.zig:53-55) */
+    uint32_t num_components;
+    uint32_t bytes_per_row;
+    uint64_t texel_offset; /* byte offset of row 0 inside wrt_scene.texels */
+} wrt_image;
+
+typedef struct wrt_scene {
+    uint32_t abi_version; /* WRT_ABI_VERSION */
+    uint32_t root;        /* entity index of Scene.scene (scene.zig:41) */
+    uint32_t lights;      /* entity index of Scene.lights (a collection) or WRT_NONE (scene.zig:42) */
+    uint32_t n_entities, n_children, n_spheres, n_quads, n_materials, n_textures, n_images;
+    const wrt_entity* entities;
+    const uint32_t* children; /* concatenated EntityCollection.entities lists (entity indices) */
+    const wrt_sphere* spheres;
+    const wrt_quad* quads;
+    const wrt_material* materials;
+    const wrt_texture* textures;
+    const wrt_image* images;
+    const uint8_t* texels;
+    uint64_t texel_bytes;
+} wrt_scene;
+
+/* The camera view the render jobs read: exactly the RenderThreadContext fields (src/render.zig:94-102)
+ * with the Viewport members they dereference (src/camera.zig:112-114).  Computed on the host in f64 by
+ * Camera.init / Viewport.init (camera.zig:61-90,117-157) so device primary rays are bit-identical. */
+typedef struct wrt_camera {
+    double position[3];
+    double pixel00_loc[3];
+    double pixel_delta_u[3];
+    double pixel_delta_v[3];
+    double defocus_disk_u[3];
+    double defocus_disk_v[3];
+    uint32_t is_depth_of_field;
+    uint32_t _pad;
+} wrt_camera;
+
+typedef struct wrt_params {
+    uint32_t width;   /* framebuffer.num_cols */
+    uint32_t height;  /* framebuffer.num_rows */
+    uint32_t samples_per_pixel;    /* Renderer.samples_per_pixel   (--samples_per_pixel) */
+    uint32_t max_ray_bounce_depth; /* Renderer.max_ray_bounce_depth (--ray_bounce_max_depth) */
+    double background_color[3];    /* Renderer.background_color */
+    double clear_color[3];         /* Renderer.clear_color */
+    uint64_t seed;                 /* keys the counter-based RNG; the reference seeds from getrandom (rng.zig:16-26) */
+    /* sharding (multi-GPU): this context renders rows  r = row_shard_index + k*row_shard_count  only and
+     * writes them densely (row k of the output = image row r).  {0,1} = whole image. */
+    uint32_t row_shard_index;
+    uint32_t row_shard_count;
+    /* sample range [sample_begin, sample_end) of each pixel, still scaled by 1/samples_per_pixel;
+     * {0,0} means the full range.  Used for sample-range sharding / progressive accumulation. */
+    uint32_t sample_begin;
+    uint32_t sample_end;
+    uint32_t cull_mode; /* WRT_CULL_* */
+    uint32_t flags;     /* WRT_FLAG_* */
+} wrt_params;
+
+#define WRT_FLAG_NO_CLEAR 1u       /* add onto the existing framebuffer contents instead of clear_color */
+#define WRT_FLAG_DISABLE_DOF 2u    /* treat the camera as a pinhole (gate-1 dumps) */
+
+typedef struct wrt_stats {
+    uint64_t paths;          /* camera samples started */
+    uint64_t rays;           /* closest-hit queries issued by the integrator (render.zig:215) */
+    double render_ms;        /* device time of the last wrt_render* call (CUDA events) */
+    double kernel_ms;        /* device time of the path-tracing kernel alone */
+    double upload_ms;        /* host wall time of the last wrt_upload_scene */
+    uint32_t kernel_launches;/* kernels launched by the last wrt_render* call */
+    uint32_t program_ops;    /* size of the compiled traversal program */
+    uint32_t n_prims;        /* leaf primitives in DFS order */
+    uint32_t _pad;
+} wrt_stats;
+
+typedef struct wrt_ctx wrt_ctx;
+
+/* exported symbols (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define WRT_API __attribute__((visibility("default")))
+#else
+#define WRT_API
+#endif
+
+/* Lifetime ------------------------------------------------------------------------------------ */
+WRT_API int wrt_create(int cuda_device, wrt_ctx** out);
+WRT_API void wrt_destroy(wrt_ctx* ctx);
+/* Text of the most recent failure on `ctx` (or of the last failed wrt_create when ctx == NULL). */
+WRT_API const char* wrt_last_error(const wrt_ctx* ctx);
+WRT_API uint32_t wrt_abi_version(void);
+
+/* Scene --------------------------------------------------------------------------------------- */
+/* Validates the tree, assigns primitive ids (DFS order), compiles the stack-less
+ * traversal program and copies everything to the device. */
+WRT_API int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene);
+
+/* Render (replaces Renderer.render, src/render.zig:29-74) ------------------------------------- */
+/* Host framebuffer: `framebuffer` points at Framebuffer.buffer ([]Color, camera.zig:14); one pixel every
+ * `pixel_stride_bytes` bytes (= @sizeOf(Vec3): 32 with 4 lanes, 64 with 8; >= 24), lanes 0..2 = R,G,B
+ * linear radiance, remaining lanes written as 0.  Result per pixel: clear_color + mean of rayColor. */
+WRT_API int wrt_render(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* framebuffer,
+               size_t pixel_stride_bytes);
+/* Same, but `d_framebuffer` is a device pointer on the context's device (dense rows of this shard);
+ * no device->host copy is made.  Used under NCCL gathers. */
+WRT_API int wrt_render_device(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* d_framebuffer,
+                      size_t pixel_stride_bytes);
+/* Quantise the frame produced by the last wrt_render* call exactly like encodeColor
+ * (src/writer/writer.zig:68-94: NaN->0, sqrt, clamp [0,0.999], *256, truncate) into 3 bytes/pixel (host). */
+WRT_API int wrt_encode_rgb8(wrt_ctx* ctx, uint8_t* rgb_out);
+
+/* Gates / diagnostics ------------------------------------------------------------------------- */
+/* Gate 1: closest hit of the PRIMARY ray of samples [0, n_samples) of every pixel (row-major, sample
+ * innermost): primitive id (WRT_NONE = miss) and t.  Depth of field is disabled. */
+WRT_API int wrt_primary_hits(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, uint32_t n_samples,
+                     uint32_t* prim_ids, double* t);
+/* Closest hit of arbitrary rays against the uploaded scene with range (tmin, +inf):
+ * origins/directions are n xyz triples; outputs may be NULL.  point/normal are n xyz triples. */
+WRT_API int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double* directions, uint64_t n, double tmin,
+                   uint32_t cull_mode, uint32_t* prim_ids, double* t, double* point, double* normal,
+                   double* uv, uint32_t* front_face);
+/* Sobol pixel sampling (src/math/sampler.zig:197-201,222-234,267-298): for each listed pixel and sample
+ * index returns the global Sobol index and the [0,1) pixel offsets. */
+WRT_API int wrt_sobol_pixel_samples(wrt_ctx* ctx, uint32_t width, uint32_t height, const uint32_t* cols,
+                            const uint32_t* rows, const uint32_t* sample_idx, uint64_t n, uint64_t* sobol_index,
+                            double* offsets_xy);
+/* Sobol higher dimensions (sampler.zig:203-247): sampleDimension(dim) for a given global index with the
+ * noop or owen_fast randomiser (Murmur2 per-dimension seed + Laine-Karras hash, sampler.zig:39-53). */
+WRT_API int wrt_sobol_dimension_samples(wrt_ctx* ctx, const uint64_t* sobol_index, const uint32_t* dimension,
+                                uint64_t n, uint32_t owen_fast, uint32_t seed, float* out);
+WRT_API int wrt_get_stats(const wrt_ctx* ctx, wrt_stats* out);
+/* Measures the device's binary64 FMA issue rate (thread-level DFMA per second) with a micro-kernel: the denominator of
+ * the issue-bound roofline for the cache-resident configs. */
+WRT_API int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WRT_H */

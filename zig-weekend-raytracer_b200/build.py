@@ -1,0 +1,87 @@
+"""In-tree build of the native pieces.
+
+  libwrt.so   the product: CUDA kernels + C ABI (csrc/), nvcc, sm_100a only
+
+It is built next to its sources so that it travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+DATA = PKG / "data"
+LIBWRT = PKG / "libwrt.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",          # binary64 ops stay unfused in source order; culling uses explicit fma()
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA back end cannot be built (there is no CPU fallback)")
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def build_wrt(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
+    cu = [CSRC / "wrt_api.cu", CSRC / "wrt_kernels.cu", CSRC / "wrt_program.cu"]
+    deps = cu + [CSRC / "wrt_device.cuh", CSRC / "wrt_kernels.h", CSRC / "wrt_program.h", CSRC / "wrt_sobol_blob.c",
+                 ROOT / "include" / "wrt.h", DATA / "sobol_tables.bin", Path(__file__)]
+    if not force and _newer(LIBWRT, deps):
+        return LIBWRT
+    blob_o = CSRC / "wrt_sobol_blob.o"
+    cc = os.environ.get("CC", "gcc")
+    subprocess.check_call([cc, "-c", "-fPIC", "-O2", f'-DWRT_SOBOL_BLOB="{DATA / "sobol_tables.bin"}"',
+                           str(CSRC / "wrt_sobol_blob.c"), "-o", str(blob_o)])
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-shared", "-o", str(LIBWRT), *map(str, cu), str(blob_o)]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return LIBWRT
+
+
+HOST = PKG / "host"
+LIBWRTH = PKG / "libwrth.so"
+CLI = PKG / "weekend-raytracer"
+HOST_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-Wall", "-Wextra", "-pthread"]
+
+
+def build_host(force: bool = False) -> Path:
+    """Host-side mirror of the reference interface (scene construction, flattening, Renderer.render, PPM writer) as
+    libwrth.so, plus the `weekend-raytracer` command line driver.  Both link libwrt.so through $ORIGIN."""
+    lib_srcs = [HOST / n for n in ("wrh_entity.cpp", "wrh_scenes.cpp", "wrh_render.cpp", "wrh_writer.cpp", "wrh_capi.cpp")]
+    hdrs = [HOST / n for n in ("wrh_math.hpp", "wrh_rng.hpp", "wrh_scene.hpp", "wrh_writer.hpp")] + [ROOT / "include" / "wrt.h"]
+    cxx = os.environ.get("CXX", "g++")
+    link = [f"-L{PKG}", "-lwrt", "-Wl,-rpath,$ORIGIN"]
+    if force or not _newer(LIBWRTH, lib_srcs + hdrs + [LIBWRT, Path(__file__)]):
+        subprocess.check_call([cxx, *HOST_FLAGS, "-shared", "-o", str(LIBWRTH), *map(str, lib_srcs), *link])
+    if force or not _newer(CLI, lib_srcs + hdrs + [HOST / "main.cpp", LIBWRT, Path(__file__)]):
+        subprocess.check_call([cxx, *HOST_FLAGS, "-o", str(CLI), str(HOST / "main.cpp"),
+                               *map(str, lib_srcs[:-1]), *link])
+    return LIBWRTH
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    print(build_wrt(force=force, verbose="-v" in sys.argv))
+    print(build_host(force=force))

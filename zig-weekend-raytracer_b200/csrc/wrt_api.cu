@@ -1,0 +1,637 @@
+// wrt_api.cu — the C ABI of include/wrt.h: context, scene upload, render, gates.
+// No CPU fallback exists: every entry point that needs the device returns WRT_E_CUDA when it is unavailable.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "wrt_device.cuh"
+#include "wrt_kernels.h"
+#include "wrt_program.h"
+
+extern "C" const unsigned char wrt_sobol_blob[];
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;  // capacity in elements
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+        cudaError_t e = ensure(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+struct SobolBlob {
+    const uint32_t* matrices32;  // [1024*52]
+    const uint64_t* vdc;         // [25][52]
+    const uint64_t* vdc_inv;     // [26][52]
+    uint32_t n_dims, matrix_size, n_vdc, n_vdc_inv;
+};
+
+bool parse_sobol_blob(SobolBlob& b) {
+    if (std::memcmp(wrt_sobol_blob, "WRTSOBL1", 8) != 0) return false;
+    uint32_t hdr[4];
+    std::memcpy(hdr, wrt_sobol_blob + 8, sizeof hdr);
+    b.n_dims = hdr[0]; b.matrix_size = hdr[1]; b.n_vdc = hdr[2]; b.n_vdc_inv = hdr[3];
+    if (b.n_dims != 1024 || b.matrix_size != 52 || b.n_vdc != 25 || b.n_vdc_inv != 26) return false;
+    b.matrices32 = reinterpret_cast<const uint32_t*>(wrt_sobol_blob + 24);
+    b.vdc = reinterpret_cast<const uint64_t*>(wrt_sobol_blob + 24 + 4ull * b.n_dims * b.matrix_size);
+    b.vdc_inv = b.vdc + (size_t)b.n_vdc * b.matrix_size;
+    return true;
+}
+
+uint32_t ceil_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+uint32_t log2u(uint32_t v) {
+    uint32_t l = 0;
+    while (v >>= 1) ++l;
+    return l;
+}
+
+}  // namespace
+
+struct wrt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    SobolBlob blob{};
+
+    // scene
+    bool have_scene = false;
+    wrt::CompiledScene cs;
+    wrt::DeviceScene ds{};
+    DevBuf<uint4> d_ops;
+    DevBuf<wrt::BoxRef> d_boxes_ref;
+    DevBuf<wrt::BoxTight> d_boxes_tight;
+    DevBuf<wrt::SphereGeom> d_spheres;
+    DevBuf<wrt::SphereAux> d_sphere_aux;
+    DevBuf<wrt::QuadGeom> d_quads;
+    DevBuf<wrt::Xform> d_xforms;
+    DevBuf<wrt::Material> d_materials;
+    DevBuf<wrt::Texture> d_textures;
+    DevBuf<wrt::ImageDesc> d_images;
+    DevBuf<wrt::Light> d_lights;
+    DevBuf<uint32_t> d_sobol_matrices;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+
+    // render state
+    DevBuf<double> d_accum;
+    DevBuf<double> d_fb;
+    DevBuf<uint8_t> d_rgb8;
+    DevBuf<unsigned long long> d_counters;
+    uint32_t last_pixels = 0;        // pixels of the last render (this shard)
+    bool last_valid = false;
+    uint32_t sobol_w = 0, sobol_h = 0;  // resolution the constant Sobol tables were loaded for
+    wrt::SobolTables sobol_staging{};
+    wrt_stats stats{};
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return WRT_E_CUDA;
+    }
+    void free_images() {
+        for (auto t : texobjs) cudaDestroyTextureObject(t);
+        for (auto a : arrays) cudaFreeArray(a);
+        texobjs.clear();
+        arrays.clear();
+    }
+};
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); \
+    } while (0)
+
+static int bind_device(wrt_ctx* ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "cudaSetDevice");
+    return WRT_OK;
+}
+
+extern "C" uint32_t wrt_abi_version(void) { return WRT_ABI_VERSION; }
+
+extern "C" const char* wrt_last_error(const wrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int wrt_create(int cuda_device, wrt_ctx** out) {
+    if (!out) { g_create_error = "wrt_create: out is NULL"; return WRT_E_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("wrt_create: no CUDA device (") + cudaGetErrorString(e) + "); this back end has no CPU fallback";
+        return WRT_E_CUDA;
+    }
+    if (cuda_device < 0 || cuda_device >= count) { g_create_error = "wrt_create: device index out of range"; return WRT_E_INVALID; }
+    wrt_ctx* ctx = new (std::nothrow) wrt_ctx();
+    if (!ctx) { g_create_error = "wrt_create: out of host memory"; return WRT_E_NOMEM; }
+    ctx->device = cuda_device;
+    auto bail = [&](cudaError_t ce, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        wrt_destroy(ctx);
+        return WRT_E_CUDA;
+    };
+    if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        g_create_error = "wrt_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        wrt_destroy(ctx);
+        return WRT_E_CUDA;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if (!parse_sobol_blob(ctx->blob)) {
+        g_create_error = "wrt_create: embedded Sobol table blob is corrupt";
+        wrt_destroy(ctx);
+        return WRT_E_INVALID;
+    }
+    if ((e = ctx->d_counters.ensure(4)) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
+    *out = ctx;
+    return WRT_OK;
+}
+
+extern "C" void wrt_destroy(wrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->free_images();
+    ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_spheres.release();
+    ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_materials.release();
+    ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release();
+    ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// Image textures as CUDA texture objects: uchar4 texels, point sampling, unnormalised coordinates, clamped —
+// Image.getPixel's clamped fetch (image.zig:23-36).  pixelToColor reads bytes 0..2 of a num_components-wide
+// pixel (texture.zig:70-77), which for 1- and 2-component images runs into the next pixel;
+// the RGBA staging copy reproduces exactly those bytes.
+static int upload_images(wrt_ctx* ctx, const wrt_scene* sc) {
+    ctx->free_images();
+    std::vector<wrt::ImageDesc> descs(sc->n_images);
+    for (uint32_t i = 0; i < sc->n_images; ++i) {
+        const wrt_image& im = sc->images[i];
+        wrt::ImageDesc d;
+        d.tex = 0; d.width = im.width; d.height = im.height;
+        if (im.height == 0 || im.width == 0) { d.height = 0; descs[i] = d; continue; }
+        const uint64_t need = im.texel_offset + (uint64_t)im.bytes_per_row * im.height;
+        if (!sc->texels || need > sc->texel_bytes || im.num_components == 0 || (uint64_t)im.width * im.num_components > im.bytes_per_row)
+            return ctx->fail(WRT_E_INVALID, "image texel range out of bounds");
+        std::vector<uchar4> rgba((size_t)im.width * im.height);
+        const uint8_t* base = sc->texels + im.texel_offset;
+        const uint64_t total = (uint64_t)im.bytes_per_row * im.height;
+        for (uint32_t y = 0; y < im.height; ++y)
+            for (uint32_t x = 0; x < im.width; ++x) {
+                uint64_t o = (uint64_t)im.bytes_per_row * y + (uint64_t)im.num_components * x;
+                uchar4 px;
+                px.x = base[o];
+                px.y = (o + 1 < total) ? base[o + 1] : 0;
+                px.z = (o + 2 < total) ? base[o + 2] : 0;
+                px.w = 255;
+                rgba[(size_t)y * im.width + x] = px;
+            }
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        CU(cudaMallocArray(&arr, &fmt, im.width, im.height));
+        ctx->arrays.push_back(arr);
+        CU(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)im.width * sizeof(uchar4), (size_t)im.width * sizeof(uchar4), im.height,
+                               cudaMemcpyHostToDevice));
+        cudaResourceDesc res;
+        std::memset(&res, 0, sizeof res);
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        CU(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        ctx->texobjs.push_back(tex);
+        d.tex = tex;
+        descs[i] = d;
+    }
+    CU(ctx->d_images.upload(descs, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // descs is a local
+    return WRT_OK;
+}
+
+extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    ctx->have_scene = false;
+    ctx->last_valid = false;
+    std::string err;
+    rc = wrt::compile_scene(scene, ctx->cs, err);
+    if (rc != WRT_OK) return ctx->fail(rc, "wrt_upload_scene: " + err);
+    rc = upload_images(ctx, scene);
+    if (rc != WRT_OK) return rc;
+    wrt::CompiledScene& cs = ctx->cs;
+    CU(ctx->d_ops.upload(cs.ops, ctx->stream));
+    CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
+    CU(ctx->d_boxes_tight.upload(cs.boxes_tight, ctx->stream));
+    CU(ctx->d_spheres.upload(cs.spheres, ctx->stream));
+    CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
+    CU(ctx->d_quads.upload(cs.quads, ctx->stream));
+    CU(ctx->d_xforms.upload(cs.xforms, ctx->stream));
+    CU(ctx->d_materials.upload(cs.materials, ctx->stream));
+    CU(ctx->d_textures.upload(cs.textures, ctx->stream));
+    CU(ctx->d_lights.upload(cs.lights, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    wrt::DeviceScene& ds = ctx->ds;
+    ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p;
+    ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
+    ds.xforms = ctx->d_xforms.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
+    ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p;
+    ds.n_ops = (uint32_t)cs.ops.size();
+    ds.n_lights = (uint32_t)cs.lights.size();
+    ds.has_lights = cs.has_lights ? 1u : 0u;
+    ds.has_moving = cs.has_moving ? 1u : 0u;
+    ctx->have_scene = true;
+    ctx->stats.program_ops = ds.n_ops;
+    ctx->stats.n_prims = cs.n_prims;
+    ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return WRT_OK;
+}
+
+// Load the constant-memory Sobol tables for a W x H framebuffer (scale = ceilPowerOfTwo(max(W,H)), sampler.zig:188).
+static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
+    if (ctx->sobol_w == width && ctx->sobol_h == height) return WRT_OK;
+    if (width == 0 || height == 0) return ctx->fail(WRT_E_INVALID, "image dimensions must be non-zero");
+    const uint32_t mx = width > height ? width : height;
+    if (mx > (1u << 26)) return ctx->fail(WRT_E_LIMIT, "image side exceeds the Sobol table range (2^26)");
+    wrt::SobolTables& t = ctx->sobol_staging;  // staging outlives the async copy; synchronised below
+    std::memset(&t, 0, sizeof t);
+    t.scale = ceil_pow2(mx);
+    t.log2_scale = log2u(t.scale);
+    if (t.log2_scale > 0) {
+        std::memcpy(t.vdc, ctx->blob.vdc + (size_t)(t.log2_scale - 1) * 52, sizeof t.vdc);
+        std::memcpy(t.vdc_inv, ctx->blob.vdc_inv + (size_t)(t.log2_scale - 1) * 52, sizeof t.vdc_inv);
+    }
+    std::memcpy(t.dim0, ctx->blob.matrices32, sizeof t.dim0);
+    std::memcpy(t.dim1, ctx->blob.matrices32 + 52, sizeof t.dim1);
+    CU(wrt::upload_sobol_tables(t, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->sobol_w = width; ctx->sobol_h = height;
+    return WRT_OK;
+}
+
+static uint32_t shard_rows(const wrt_params& p) {
+    if (p.row_shard_index >= p.height) return 0;
+    return (p.height - p.row_shard_index + p.row_shard_count - 1) / p.row_shard_count;
+}
+
+static int normalise_params(wrt_ctx* ctx, const wrt_params* in, wrt_params& p) {
+    if (!in) return ctx->fail(WRT_E_INVALID, "params is NULL");
+    p = *in;
+    if (p.row_shard_count == 0) p.row_shard_count = 1;
+    if (p.sample_begin == 0 && p.sample_end == 0) p.sample_end = p.samples_per_pixel;
+    if (p.width == 0 || p.height == 0) return ctx->fail(WRT_E_INVALID, "image dimensions must be non-zero");
+    if ((uint64_t)p.width * p.height > 0xFFFFFFFFull) return ctx->fail(WRT_E_LIMIT, "more than 2^32 pixels");
+    if (p.samples_per_pixel == 0) return ctx->fail(WRT_E_INVALID, "samples_per_pixel must be non-zero");
+    if (p.sample_begin > p.sample_end) return ctx->fail(WRT_E_INVALID, "sample_begin > sample_end");
+    if (p.row_shard_index >= p.row_shard_count) return ctx->fail(WRT_E_INVALID, "row_shard_index >= row_shard_count");
+    if (p.cull_mode > WRT_CULL_REFERENCE) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    return WRT_OK;
+}
+
+static void fill_constants(const wrt_camera& cam, const wrt_params& p, wrt::RenderConstants& rc) {
+    std::memset(&rc, 0, sizeof rc);
+    rc.cam = cam;
+    for (int k = 0; k < 3; ++k) rc.background[k] = p.background_color[k];
+    rc.seed = p.seed;
+    rc.width = p.width; rc.height = p.height; rc.spp = p.samples_per_pixel; rc.max_depth = p.max_ray_bounce_depth;
+    rc.dof = (cam.is_depth_of_field && !(p.flags & WRT_FLAG_DISABLE_DOF)) ? 1u : 0u;
+    rc.row_shard_index = p.row_shard_index; rc.row_shard_count = p.row_shard_count;
+    rc.n_rows_local = shard_rows(p);
+    rc.n_col_blocks = (p.width + 31u) / 32u;
+    rc.sample_begin = p.sample_begin; rc.sample_end = p.sample_end;
+}
+
+// Shared body of wrt_render / wrt_render_device.  `d_out` is a device pointer or NULL (internal buffer + D2H).
+static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* host_fb, void* d_out, size_t stride) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!ctx->have_scene) return ctx->fail(WRT_E_STATE, "wrt_render: no scene uploaded");
+    if (!cam) return ctx->fail(WRT_E_INVALID, "camera is NULL");
+    if (!host_fb && !d_out) return ctx->fail(WRT_E_INVALID, "framebuffer is NULL");
+    if (stride < 24 || stride % 8) return ctx->fail(WRT_E_INVALID, "pixel_stride_bytes must be a multiple of 8 and >= 24");
+    wrt_params p;
+    rc_ = normalise_params(ctx, params, p);
+    if (rc_) return rc_;
+    rc_ = prepare_sobol(ctx, p.width, p.height);
+    if (rc_) return rc_;
+
+    wrt::RenderConstants rc;
+    fill_constants(*cam, p, rc);
+    const uint32_t stride_d = (uint32_t)(stride / 8);
+    const uint64_t n_pixels64 = (uint64_t)rc.n_rows_local * p.width;
+    const uint32_t n_pixels = (uint32_t)n_pixels64;
+    const uint32_t n_samples = p.sample_end - p.sample_begin;
+
+    // Job decomposition: (row x 32-column block) as in the reference (render.zig:55-73), times a sample split
+    // chosen so that the persistent grid has >= 16 jobs per resident warp to balance uneven path lengths.
+    int blocks_per_sm = 0;
+    CU(wrt::render_occupancy(p.cull_mode, &blocks_per_sm));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
+    const uint64_t resident_warps = (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
+    const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
+    uint32_t n_chunks = 1;
+    if (base_jobs > 0 && n_samples > 0) {
+        uint64_t want = (16 * resident_warps + base_jobs - 1) / base_jobs;
+        if (want < 1) want = 1;
+        if (want > 64) want = 64;
+        if (want > n_samples) want = n_samples;
+        n_chunks = (uint32_t)want;
+    }
+    rc.chunk_size = n_samples ? (n_samples + n_chunks - 1) / n_chunks : 1;
+    if (rc.chunk_size == 0) rc.chunk_size = 1;
+    rc.n_chunks = n_samples ? (n_samples + rc.chunk_size - 1) / rc.chunk_size : 0;
+    rc.total_jobs = (unsigned long long)rc.n_chunks * base_jobs;
+
+    CU(ctx->d_accum.ensure((size_t)std::max<uint32_t>(rc.n_chunks, 1) * n_pixels64 * 3));
+    CU(ctx->d_rgb8.ensure((size_t)n_pixels64 * 3));
+    double* d_fb = static_cast<double*>(d_out);
+    if (!d_fb) {
+        CU(ctx->d_fb.ensure((size_t)n_pixels64 * stride_d));
+        d_fb = ctx->d_fb.p;
+        if (p.flags & WRT_FLAG_NO_CLEAR)
+            CU(cudaMemcpyAsync(d_fb, host_fb, (size_t)n_pixels64 * stride, cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(wrt::upload_render_constants(rc, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    uint32_t launches = 0;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (rc.total_jobs > 0) {
+        CU(wrt::launch_render(ctx->ds, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        ++launches;
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(wrt::launch_resolve(ctx->d_accum.p, rc.n_chunks, n_pixels, p.clear_color, (p.flags & WRT_FLAG_NO_CLEAR) ? 1 : 0, d_fb, stride_d,
+                           ctx->d_rgb8.p, ctx->stream));
+    if (n_pixels) ++launches;
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(counters, ctx->d_counters.p, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!d_out) CU(cudaMemcpyAsync(host_fb, d_fb, (size_t)n_pixels64 * stride, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+
+    float ms_total = 0, ms_kernel = 0;
+    CU(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[3]));
+    CU(cudaEventElapsedTime(&ms_kernel, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.rays = counters[1];
+    ctx->stats.paths = counters[2];
+    ctx->stats.render_ms = ms_total;
+    ctx->stats.kernel_ms = ms_kernel;
+    ctx->stats.kernel_launches = launches;
+    ctx->last_pixels = n_pixels;
+    ctx->last_valid = true;
+    return WRT_OK;
+}
+
+extern "C" int wrt_render(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* framebuffer, size_t pixel_stride_bytes) {
+    if (!ctx) return WRT_E_INVALID;
+    if (!framebuffer) return ctx->fail(WRT_E_INVALID, "framebuffer is NULL");
+    return render_impl(ctx, cam, params, framebuffer, nullptr, pixel_stride_bytes);
+}
+
+extern "C" int wrt_render_device(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* d_framebuffer,
+                                 size_t pixel_stride_bytes) {
+    if (!ctx) return WRT_E_INVALID;
+    if (!d_framebuffer) return ctx->fail(WRT_E_INVALID, "d_framebuffer is NULL");
+    return render_impl(ctx, cam, params, nullptr, d_framebuffer, pixel_stride_bytes);
+}
+
+extern "C" int wrt_encode_rgb8(wrt_ctx* ctx, uint8_t* rgb_out) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!ctx->last_valid) return ctx->fail(WRT_E_STATE, "wrt_encode_rgb8: no frame rendered yet");
+    if (!rgb_out) return ctx->fail(WRT_E_INVALID, "rgb_out is NULL");
+    // the resolve pass already quantised the frame (fused final pass); just fetch it
+    CU(cudaMemcpyAsync(rgb_out, ctx->d_rgb8.p, (size_t)ctx->last_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return WRT_OK;
+}
+
+extern "C" int wrt_primary_hits(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, uint32_t n_samples, uint32_t* prim_ids,
+                                double* t) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!ctx->have_scene) return ctx->fail(WRT_E_STATE, "wrt_primary_hits: no scene uploaded");
+    if (!cam) return ctx->fail(WRT_E_INVALID, "camera is NULL");
+    wrt_params p;
+    rc_ = normalise_params(ctx, params, p);
+    if (rc_) return rc_;
+    rc_ = prepare_sobol(ctx, p.width, p.height);
+    if (rc_) return rc_;
+    wrt::RenderConstants rc;
+    fill_constants(*cam, p, rc);
+    rc.dof = 0;
+    const uint64_t total = (uint64_t)p.width * p.height * n_samples;
+    if (total == 0) return WRT_OK;
+    DevBuf<uint32_t> d_ids;
+    DevBuf<double> d_t;
+    int ret = WRT_OK;
+    do {
+        cudaError_t e;
+        if (prim_ids && (e = d_ids.ensure(total)) != cudaSuccess) { ret = ctx->cuda_fail(e, "cudaMalloc(ids)"); break; }
+        if (t && (e = d_t.ensure(total)) != cudaSuccess) { ret = ctx->cuda_fail(e, "cudaMalloc(t)"); break; }
+        if ((e = wrt::upload_render_constants(rc, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "constants"); break; }
+        uint32_t grid = (uint32_t)std::min<uint64_t>((total + 127) / 128, (uint64_t)ctx->sm_count * 32);
+        if ((e = wrt::launch_primary_hits(ctx->ds, p.cull_mode, n_samples, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr, grid,
+                                          ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "primary_hits_kernel"); break; }
+        if (prim_ids && (e = cudaMemcpyAsync(prim_ids, d_ids.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "D2H ids"); break; }
+        if (t && (e = cudaMemcpyAsync(t, d_t.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "D2H t"); break; }
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "primary_hits sync"); break; }
+    } while (0);
+    d_ids.release();
+    d_t.release();
+    return ret;
+}
+
+extern "C" int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double* directions, uint64_t n, double tmin, uint32_t cull_mode,
+                              uint32_t* prim_ids, double* t, double* point, double* normal, double* uv, uint32_t* front_face) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!ctx->have_scene) return ctx->fail(WRT_E_STATE, "wrt_trace_rays: no scene uploaded");
+    if (cull_mode > WRT_CULL_REFERENCE) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    if (n == 0) return WRT_OK;
+    if (!origins || !directions) return ctx->fail(WRT_E_INVALID, "origins/directions is NULL");
+    DevBuf<double> d_o, d_d, d_t, d_p, d_n, d_uv;
+    DevBuf<uint32_t> d_ids, d_ff;
+    int ret = WRT_OK;
+    do {
+        cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) { ret = ctx->cuda_fail(e, #x); break; }
+        TRY(d_o.ensure(3 * n)); TRY(d_d.ensure(3 * n));
+        if (prim_ids) TRY(d_ids.ensure(n));
+        if (t) TRY(d_t.ensure(n));
+        if (point) TRY(d_p.ensure(3 * n));
+        if (normal) TRY(d_n.ensure(3 * n));
+        if (uv) TRY(d_uv.ensure(2 * n));
+        if (front_face) TRY(d_ff.ensure(n));
+        TRY(cudaMemcpyAsync(d_o.p, origins, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(cudaMemcpyAsync(d_d.p, directions, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        uint32_t grid = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * 32);
+        TRY(wrt::launch_trace_rays(ctx->ds, cull_mode, d_o.p, d_d.p, n, tmin, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr,
+                                   point ? d_p.p : nullptr, normal ? d_n.p : nullptr, uv ? d_uv.p : nullptr,
+                                   front_face ? d_ff.p : nullptr, grid, ctx->stream));
+        if (prim_ids) TRY(cudaMemcpyAsync(prim_ids, d_ids.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (t) TRY(cudaMemcpyAsync(t, d_t.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (point) TRY(cudaMemcpyAsync(point, d_p.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (normal) TRY(cudaMemcpyAsync(normal, d_n.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (uv) TRY(cudaMemcpyAsync(uv, d_uv.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (front_face) TRY(cudaMemcpyAsync(front_face, d_ff.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(cudaStreamSynchronize(ctx->stream));
+#undef TRY
+    } while (0);
+    d_o.release(); d_d.release(); d_t.release(); d_p.release(); d_n.release(); d_uv.release(); d_ids.release(); d_ff.release();
+    return ret;
+}
+
+extern "C" int wrt_sobol_pixel_samples(wrt_ctx* ctx, uint32_t width, uint32_t height, const uint32_t* cols, const uint32_t* rows,
+                                       const uint32_t* sample_idx, uint64_t n, uint64_t* sobol_index, double* offsets_xy) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (n == 0) return WRT_OK;
+    if (!cols || !rows || !sample_idx) return ctx->fail(WRT_E_INVALID, "cols/rows/sample_idx is NULL");
+    rc_ = prepare_sobol(ctx, width, height);
+    if (rc_) return rc_;
+    DevBuf<uint32_t> d_c, d_r, d_s;
+    DevBuf<uint64_t> d_i;
+    DevBuf<double> d_o;
+    int ret = WRT_OK;
+    do {
+        cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) { ret = ctx->cuda_fail(e, #x); break; }
+        TRY(d_c.ensure(n)); TRY(d_r.ensure(n)); TRY(d_s.ensure(n));
+        if (sobol_index) TRY(d_i.ensure(n));
+        if (offsets_xy) TRY(d_o.ensure(2 * n));
+        TRY(cudaMemcpyAsync(d_c.p, cols, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(cudaMemcpyAsync(d_r.p, rows, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(cudaMemcpyAsync(d_s.p, sample_idx, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(wrt::launch_sobol_pixel(d_c.p, d_r.p, d_s.p, n, sobol_index ? d_i.p : nullptr, offsets_xy ? d_o.p : nullptr, ctx->stream));
+        if (sobol_index) TRY(cudaMemcpyAsync(sobol_index, d_i.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (offsets_xy) TRY(cudaMemcpyAsync(offsets_xy, d_o.p, 2 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(cudaStreamSynchronize(ctx->stream));
+#undef TRY
+    } while (0);
+    d_c.release(); d_r.release(); d_s.release(); d_i.release(); d_o.release();
+    return ret;
+}
+
+extern "C" int wrt_sobol_dimension_samples(wrt_ctx* ctx, const uint64_t* sobol_index, const uint32_t* dimension, uint64_t n,
+                                           uint32_t owen_fast, uint32_t seed, float* out) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (n == 0) return WRT_OK;
+    if (!sobol_index || !dimension || !out) return ctx->fail(WRT_E_INVALID, "argument is NULL");
+    for (uint64_t i = 0; i < n; ++i)
+        if (dimension[i] >= 1024) return ctx->fail(WRT_E_INVALID, "Sobol dimension >= NSobolDimensions (1024)");
+    DevBuf<uint64_t> d_i;
+    DevBuf<uint32_t> d_d;
+    DevBuf<float> d_o;
+    int ret = WRT_OK;
+    do {
+        cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) { ret = ctx->cuda_fail(e, #x); break; }
+        if (!ctx->d_sobol_matrices.p) {
+            TRY(ctx->d_sobol_matrices.ensure(1024 * 52));
+            TRY(cudaMemcpyAsync(ctx->d_sobol_matrices.p, ctx->blob.matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        TRY(d_i.ensure(n)); TRY(d_d.ensure(n)); TRY(d_o.ensure(n));
+        TRY(cudaMemcpyAsync(d_i.p, sobol_index, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(cudaMemcpyAsync(d_d.p, dimension, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(wrt::launch_sobol_dimension(ctx->d_sobol_matrices.p, d_i.p, d_d.p, n, owen_fast, seed, d_o.p, ctx->stream));
+        TRY(cudaMemcpyAsync(out, d_o.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(cudaStreamSynchronize(ctx->stream));
+#undef TRY
+    } while (0);
+    d_i.release(); d_d.release(); d_o.release();
+    return ret;
+}
+
+extern "C" int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!fma_per_second) return ctx->fail(WRT_E_INVALID, "fma_per_second is NULL");
+    const uint32_t block = 256, grid = (uint32_t)ctx->sm_count * 8, iters = 1u << 16;
+    DevBuf<double> d_out;
+    int ret = WRT_OK;
+    do {
+        cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) { ret = ctx->cuda_fail(e, #x); break; }
+        TRY(d_out.ensure((size_t)grid * block));
+        TRY(wrt::launch_fp64_peak(d_out.p, grid, block, 1u << 10, ctx->stream));  // warm-up
+        double best = 0.0;
+        for (int rep = 0; rep < 5; ++rep) {
+            TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+            TRY(wrt::launch_fp64_peak(d_out.p, grid, block, iters, ctx->stream));
+            TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+            TRY(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+            double rate = (double)grid * block * iters * 8.0 / (ms * 1e-3);
+            if (rate > best) best = rate;
+        }
+        if (ret == WRT_OK) *fma_per_second = best;
+#undef TRY
+    } while (0);
+    d_out.release();
+    return ret;
+}
+
+extern "C" int wrt_get_stats(const wrt_ctx* ctx, wrt_stats* out) {
+    if (!ctx || !out) return WRT_E_INVALID;
+    *out = ctx->stats;
+    return WRT_OK;
+}

@@ -1,0 +1,612 @@
+// wrt_device.cuh — device-side data layout and arithmetic of the B200 render back end.
+//
+// Everything here follows the behavioural spec of the reference's hot path; each
+// function cites the reference lines it replaces.  The translation unit is compiled with -fmad=false so that
+// binary64 operations stay unfused in source order (the reference emits no FMA); the places
+// where exactness is irrelevant (conservative culling) call fma() explicitly.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/wrt.h"
+
+namespace wrt {
+
+// ---------------------------------------------------------------------------------------------------------
+// Device scene layout.  All records are 16-byte aligned and read with 128-bit loads.
+// ---------------------------------------------------------------------------------------------------------
+
+// Traversal program: the entity tree in DFS pre-order (= the reference's visiting order: bvh_node.hit tests
+// left then right, entity.zig:286-303; collections scan in insertion order, :351-367).  Stack-less: a culled
+// node jumps to `skip`, the first op after its subtree.
+enum OpKind : uint32_t {
+    OP_NODE = 0,        // x=kind, y=box index, z=skip pc
+    OP_SPHERE = 1,      // y=sphere index, z=material, w=prim id
+    OP_QUAD = 2,        // y=quad index,   z=material, w=prim id
+    OP_PUSH_TRANSLATE = 3,  // y=xform index
+    OP_PUSH_ROTATE_Y = 4,   // y=xform index
+    OP_POP = 5,         // y=parent xform index (WRT_NONE = world)
+    OP_END = 6,
+    OP_NODE_TIGHT_ONLY = 7  // like OP_NODE but inserted by the compiler (instance bounds); REFERENCE culling ignores it
+};
+
+struct __align__(16) BoxRef {   // the reference's cached AABB.min/max, x and y only (aabb.zig:80-101 as executed)
+    double min_x, min_y, max_x, max_y;
+};
+struct __align__(16) BoxTight { // recomputed conservative box, slab pairs
+    double2 x, y, z;            // (min,max) per axis
+};
+struct __align__(16) SphereGeom { // entity.zig:536-537
+    double cx, cy, cz, radius;
+};
+struct __align__(16) SphereAux {  // moving spheres only (entity.zig:541-542)
+    double mx, my, mz;
+    uint32_t is_moving, _pad;
+};
+struct __align__(16) QuadGeom {   // entity.zig:431-441
+    double nx, ny, nz, offset;    // unit normal, D
+    double sx, sy, sz, area;      // start point, area
+    double ux, uy, uz, _p0;       // basis.u
+    double vx, vy, vz, _p1;       // basis.v
+    double wx, wy, wz, _p2;       // basis.w
+};
+struct __align__(16) Xform {      // Translate / RotateY chain (entity.zig:68-205)
+    double a, b, c;               // translate: offset xyz; rotate_y: sin, cos, 0
+    uint32_t kind;                // OP_PUSH_TRANSLATE / OP_PUSH_ROTATE_Y
+    uint32_t parent;              // enclosing xform or WRT_NONE
+};
+struct __align__(16) Material {   // material.zig:79-226
+    double ar, ag, ab, param;     // metal albedo; fuzz / refraction index
+    uint32_t kind, texture, _p0, _p1;
+};
+struct __align__(16) Texture {    // texture.zig:33-119
+    double r, g, b, inv_scale;
+    uint32_t kind, even, odd, image;
+};
+struct ImageDesc {                // image.zig:23-36
+    cudaTextureObject_t tex;      // uchar4 texels, point sampled, unnormalised coordinates
+    uint32_t width, height;
+};
+struct Light {                    // Scene.lights children (entity.zig:371-386)
+    uint32_t kind;                // WRT_ENT_SPHERE / WRT_ENT_QUAD / other (pdf 0, direction (1,0,0))
+    uint32_t index;
+};
+
+struct DeviceScene {
+    const uint4* ops;
+    const BoxRef* boxes_ref;
+    const BoxTight* boxes_tight;
+    const SphereGeom* spheres;
+    const SphereAux* sphere_aux;
+    const QuadGeom* quads;
+    const Xform* xforms;
+    const Material* materials;
+    const Texture* textures;
+    const ImageDesc* images;
+    const Light* lights;
+    uint32_t n_ops, n_lights, has_lights, has_moving;
+};
+
+struct SobolTables {               // live part of sobolmatrices.zig for one resolution
+    uint64_t vdc[52];              // VdCSobolMatrices[m-1]
+    uint64_t vdc_inv[52];          // VdCSobolMatricesInv[m-1]
+    uint32_t dim0[52];             // SobolMatrices32[0*52 ..]
+    uint32_t dim1[52];             // SobolMatrices32[1*52 ..]
+    uint32_t log2_scale, scale;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Vector arithmetic (math.zig)
+// ---------------------------------------------------------------------------------------------------------
+struct d3 { double x, y, z; };
+
+__device__ __forceinline__ d3 mk(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, d3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ d3 operator/(d3 a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ d3 operator-(d3 a) { return mk(-a.x, -a.y, -a.z); }
+// math.zig:243-246: (x0*y0 + x1*y1) + x2*y2
+__device__ __forceinline__ double dot(d3 u, d3 v) { return (u.x * v.x + u.y * v.y) + u.z * v.z; }
+// math.zig:214-229
+__device__ __forceinline__ d3 cross(d3 u, d3 v) {
+    return mk(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+__device__ __forceinline__ double length(d3 u) { return sqrt(dot(u, u)); }              // math.zig:254-256
+__device__ __forceinline__ d3 normalize(d3 u) { return u * (1.0 / length(u)); }          // math.zig:262-264
+__device__ __forceinline__ d3 reflect(d3 v, d3 n) { return v - n * (2.0 * dot(v, n)); }  // math.zig:270-272
+// math.zig:274-279
+__device__ __forceinline__ d3 refract(d3 vn, d3 n, double index) {
+    double cos_theta = fmin(dot(-vn, n), 1.0);
+    d3 perp = (vn + n * cos_theta) * index;
+    d3 par = n * (-sqrt(fabs(1.0 - dot(perp, perp))));
+    return perp + par;
+}
+__device__ __forceinline__ double clamp01(double v) { return fmax(0.0, fmin(v, 1.0)); }
+
+struct Onb { d3 u, v, w; };  // math.zig:58-96
+__device__ __forceinline__ Onb onb_init(d3 n) {  // math.zig:65-73
+    Onb b;
+    b.w = normalize(n);
+    d3 a = (fabs(b.w.y) > 0.9) ? mk(1, 0, 0) : mk(0, 1, 0);
+    b.u = normalize(cross(b.w, a));
+    b.v = cross(b.w, b.u);
+    return b;
+}
+__device__ __forceinline__ d3 onb_transform(const Onb& b, d3 p) {  // math.zig:89-95
+    return (b.u * p.x + b.v * p.y) + b.w * p.z;
+}
+
+#define WRT_PI 3.14159265358979323846264338327950288
+
+// ---------------------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10 keyed by the render seed, counted by (pixel, sample, draw).  The oracle
+// carries the same definition (oracle/wro_rng.h) so CPU and device paths consume identical numbers.
+// ---------------------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t k0, k1, pixel, sample, draw;
+};
+
+__device__ __forceinline__ uint64_t philox_bits(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t draw) {
+    uint32_t c0 = pixel, c1 = sample, c2 = draw >> 1, c3 = 0u;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return (draw & 1u) ? ((uint64_t)c2 | ((uint64_t)c3 << 32)) : ((uint64_t)c0 | ((uint64_t)c1 << 32));
+}
+__device__ __forceinline__ double rng_float(Rng& r) {  // Random.float(f64) stand-in: 53 bits in [0,1)
+    uint64_t bits = philox_bits(r.k0, r.k1, r.pixel, r.sample, r.draw++);
+    return (double)(bits >> 11) * 0x1p-53;
+}
+__device__ __forceinline__ uint32_t rng_pick(Rng& r, uint32_t n) {  // intRangeAtMost(0, n-1) stand-in
+    uint32_t i = (uint32_t)(rng_float(r) * (double)n);
+    return i < n ? i : n - 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sobol pixel sampling (sampler.zig:197-201, 222-234, 249-264, 267-298) — bit exact
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t sobol_interval_to_index(const SobolTables& T, uint64_t sample_idx, uint32_t px, uint32_t py) {
+    const uint32_t m = T.log2_scale;
+    if (m == 0) return sample_idx;
+    uint64_t index = sample_idx << (m << 1);
+    uint64_t delta = 0;
+    for (uint32_t c = 0; sample_idx > 0; sample_idx >>= 1, ++c)
+        if (sample_idx & 1) delta ^= T.vdc[c];
+    uint64_t b = ((((uint64_t)px) << m) | (uint64_t)py) ^ delta;
+    for (uint32_t c = 0; b > 0; b >>= 1, ++c)
+        if (b & 1) index ^= T.vdc_inv[c];
+    return index;
+}
+__device__ __forceinline__ float sobol_sample_bits_to_float(uint32_t v) {
+    float vf = __uint2float_rn(v);                       // @floatFromInt, round to nearest even
+    return fminf(__fmul_rn(vf, 0x1p-32f), 0x1.fffffep-1f);  // sampler.zig:262-263
+}
+__device__ __forceinline__ void sobol_pixel_2d(const SobolTables& T, uint64_t index, uint32_t px, uint32_t py, double& ox, double& oy) {
+    uint32_t v0 = 0, v1 = 0;
+    uint64_t a = index;
+    for (uint32_t i = 0; a != 0; a >>= 1, ++i) {
+        if (a & 1) { v0 ^= T.dim0[i]; v1 ^= T.dim1[i]; }
+    }
+    const double one_minus_eps = (double)0x1.fffffep-1f;
+    double rx = (double)sobol_sample_bits_to_float(v0) * (double)T.scale - (double)px;
+    double ry = (double)sobol_sample_bits_to_float(v1) * (double)T.scale - (double)py;
+    ox = fmax(0.0, fmin(rx, one_minus_eps));  // std.math.clamp, sampler.zig:229-231
+    oy = fmax(0.0, fmin(ry, one_minus_eps));
+}
+
+__device__ __forceinline__ uint32_t owen_fast_apply(uint32_t seed, uint32_t v) {  // sampler.zig:39-53
+    v = __brev(v);
+    v ^= v * 0x3d20adeau;
+    v += seed;
+    v *= (seed >> 16) | 1u;
+    v ^= v * 0x05526c56u;
+    v ^= v * 0x53a22864u;
+    return __brev(v);
+}
+__device__ __forceinline__ uint32_t murmur2_u32(uint32_t v, uint32_t seed) {  // std.hash.Murmur2_32.hashUint32WithSeed
+    const uint32_t m = 0x5bd1e995u;
+    uint32_t h1 = seed ^ 4u;
+    uint32_t k1 = v * m;
+    k1 ^= k1 >> 24;
+    k1 *= m;
+    h1 *= m;
+    h1 ^= k1;
+    h1 ^= h1 >> 13;
+    h1 *= m;
+    h1 ^= h1 >> 15;
+    return h1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Closest hit
+// ---------------------------------------------------------------------------------------------------------
+struct Ray { d3 o, d; double time; };
+
+struct HitRecord {  // hitrecord.zig:6-14
+    d3 point, normal;
+    double t, u, v;
+    uint32_t material, prim_id, front_face, is_sphere;
+    d3 sphere_outward;  // outward normal in object space, kept so the sphere UV can be computed lazily
+};
+
+// Object-space ray of transform context `xf` (chain root -> leaf), exactly as Translate.hit / RotateY.hit build
+// it (entity.zig:93-109, 169-205).  Chains are at most WRT_MAX_XFORM_DEPTH deep (checked at upload).
+#define WRT_MAX_XFORM_DEPTH 8
+__device__ __forceinline__ void apply_xform(const Xform& X, d3& o, d3& d) {
+    if (X.kind == OP_PUSH_TRANSLATE) {
+        o = o - mk(X.a, X.b, X.c);
+    } else {
+        const double sn = X.a, cs = X.b;
+        o = mk(cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z);
+        d = mk(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
+    }
+}
+__device__ inline void ray_in_xform(const DeviceScene& S, uint32_t xf, d3 wo, d3 wd, d3& o, d3& d) {
+    o = wo; d = wd;
+    if (xf == WRT_NONE) return;
+    uint32_t chain[WRT_MAX_XFORM_DEPTH];
+    int n = 0;
+    for (uint32_t k = xf; k != WRT_NONE && n < WRT_MAX_XFORM_DEPTH; k = S.xforms[k].parent) chain[n++] = k;
+    for (int i = n - 1; i >= 0; --i) apply_xform(S.xforms[chain[i]], o, d);
+}
+
+template <int CULL>
+struct Culler;
+
+// The reference's AABB.hit as executed (aabb.zig:80-101, math.zig:186-190): x and y only, each on its own,
+// true divisions, MaxMult on tmax.
+template <>
+struct Culler<WRT_CULL_REFERENCE> {
+    d3 o, d;
+    __device__ __forceinline__ void set_ray(d3 ro, d3 rd) { o = ro; d = rd; }
+    __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
+        const double2* p = reinterpret_cast<const double2*>(S.boxes_ref + box);
+        double2 mn = __ldg(p), mx = __ldg(p + 1);
+        double t0x = (mn.x - o.x) / d.x, t1x = (mx.x - o.x) / d.x;
+        double t0y = (mn.y - o.y) / d.y, t1y = (mx.y - o.y) / d.y;
+        double lox = fmax(fmin(t0x, t1x), tmin), hix = fmin(fmax(t0x, t1x), tmax) * 1.0000000000000004;
+        double loy = fmax(fmin(t0y, t1y), tmin), hiy = fmin(fmax(t0y, t1y), tmax) * 1.0000000000000004;
+        return (hix > lox) && (hiy > loy);
+    }
+};
+
+// Fast path: proper 3-axis slab intersection on recomputed, padded boxes with a per-ray reciprocal direction.
+// Culling only has to be conservative, so this is the one place that uses FMA.
+template <>
+struct Culler<WRT_CULL_TIGHT> {
+    d3 inv, oi;  // 1/d and o/d
+    // A zero (or denormal-small) direction component would make inv infinite and b*inv - o*inv an inf - inf NaN that
+    // loses the sign of (b - o); nudging it to +-1e-200 keeps every slab bound finite and correctly signed.
+    static __device__ __forceinline__ double safe_inv(double v) {
+        return 1.0 / (fabs(v) < 1e-200 ? copysign(1e-200, v) : v);
+    }
+    __device__ __forceinline__ void set_ray(d3 ro, d3 rd) {
+        inv = mk(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
+        oi = mk(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+    }
+    __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
+        const double2* p = reinterpret_cast<const double2*>(S.boxes_tight + box);
+        double2 bx = __ldg(p), by = __ldg(p + 1), bz = __ldg(p + 2);
+        double t0x = fma(bx.x, inv.x, -oi.x), t1x = fma(bx.y, inv.x, -oi.x);
+        double t0y = fma(by.x, inv.y, -oi.y), t1y = fma(by.y, inv.y, -oi.y);
+        double t0z = fma(bz.x, inv.z, -oi.z), t1z = fma(bz.y, inv.z, -oi.z);
+        // fmin/fmax drop NaNs (0 * inf), which can only widen the interval
+        double lo = fmax(fmax(fmin(t0x, t1x), fmin(t0y, t1y)), fmax(fmin(t0z, t1z), tmin));
+        double hi = fmin(fmin(fmax(t0x, t1x), fmax(t0y, t1y)), fmin(fmax(t0z, t1z), tmax));
+        return hi * 1.0000000000000004 >= lo;
+    }
+};
+
+struct ClosestHit {
+    double t;
+    uint32_t pc;     // op index of the winning primitive, WRT_NONE = miss
+    uint32_t xform;  // transform context it was hit in
+};
+
+// Sequential closest-hit scan in DFS order with the running tmax, i.e. exactly what the reference's recursion
+// computes: spheres accept tmin < t < tmax (entity.zig:608), quads tmin <= t <= tmax (:485, interval.zig:26-33),
+// so a later coincident quad replaces an earlier hit.
+template <int CULL>
+__device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
+    ClosestHit best;
+    best.t = tmax; best.pc = WRT_NONE; best.xform = WRT_NONE;
+    d3 o = wo, d = wd;
+    uint32_t xf = WRT_NONE;
+    Culler<CULL> cull;
+    cull.set_ray(o, d);
+    uint32_t pc = 0;
+    for (;;) {
+        const uint4 op = __ldg(S.ops + pc);
+        if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) {
+            bool pass = (CULL == WRT_CULL_REFERENCE && op.x == OP_NODE_TIGHT_ONLY) ? true : cull.pass(S, op.y, tmin, best.t);
+            pc = pass ? pc + 1 : op.z;
+        } else if (op.x == OP_SPHERE) {
+            // SphereEntity.hit, entity.zig:585-623
+            const double2* g = reinterpret_cast<const double2*>(S.spheres + op.y);
+            double2 g0 = __ldg(g), g1 = __ldg(g + 1);
+            d3 center = mk(g0.x, g0.y, g1.x);
+            const double radius = g1.y;
+            if (S.has_moving) {
+                const SphereAux ax = S.sphere_aux[op.y];
+                if (ax.is_moving) center = center + mk(ax.mx, ax.my, ax.mz) * time;  // entity.zig:653-656
+            }
+            d3 oc = center - o;
+            double a = dot(d, d);
+            double h = dot(d, oc);
+            double c = dot(oc, oc) - radius * radius;
+            double disc = h * h - a * c;
+            if (!(disc < 0.0)) {
+                double sq = sqrt(disc);
+                double root = (h - sq) / a;
+                bool ok = (tmin < root) && (root < best.t);
+                if (!ok) {
+                    root = (h + sq) / a;
+                    ok = (tmin < root) && (root < best.t);
+                }
+                if (ok) { best.t = root; best.pc = pc; best.xform = xf; }
+            }
+            ++pc;
+        } else if (op.x == OP_QUAD) {
+            // QuadEntity.hit, entity.zig:477-501
+            const double2* g = reinterpret_cast<const double2*>(S.quads + op.y);
+            double2 n0 = __ldg(g), n1 = __ldg(g + 1);
+            d3 n = mk(n0.x, n0.y, n1.x);
+            double denom = dot(n, d);
+            if (!(fabs(denom) < 1e-8)) {
+                double t = (n1.y - dot(n, o)) / denom;
+                if ((tmin <= t) && (t <= best.t)) {
+                    double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
+                    double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                    d3 p = o + d * t;
+                    d3 planar = p - mk(s0.x, s0.y, s1.x);
+                    d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
+                    double alpha = dot(bw, cross(planar, bv));
+                    double beta = dot(bw, cross(bu, planar));
+                    if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
+                        best.t = t; best.pc = pc; best.xform = xf;
+                    }
+                }
+            }
+            ++pc;
+        } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
+            apply_xform(S.xforms[op.y], o, d);
+            xf = op.y;
+            cull.set_ray(o, d);
+            ++pc;
+        } else if (op.x == OP_POP) {
+            xf = op.y;
+            ray_in_xform(S, xf, wo, wd, o, d);
+            cull.set_ray(o, d);
+            ++pc;
+        } else {  // OP_END
+            break;
+        }
+    }
+    return best;
+}
+
+// entity.zig:659-666 getSphereUv
+__device__ __forceinline__ void sphere_uv(d3 v, double& u_out, double& v_out) {
+    double theta = acos(-v.y);
+    double phi = atan2(-v.z, v.x) + WRT_PI;
+    u_out = phi / (2 * WRT_PI);
+    v_out = theta / WRT_PI;
+}
+
+// Rebuild the HitRecord of the winning primitive with the reference's arithmetic (entity.zig:613-620, 490-498,
+// hitrecord.zig:16-21), then carry point and normal back out through the transform chain (entity.zig:105-107,
+// 184-186).  `want_uv` = the sphere UV (acos + atan2) is only evaluated when a texture will read it.
+__device__ inline void resolve_hit(const DeviceScene& S, const ClosestHit& ch, d3 wo, d3 wd, double time, bool want_uv, HitRecord& rec) {
+    const uint4 op = __ldg(S.ops + ch.pc);
+    d3 o, d;
+    ray_in_xform(S, ch.xform, wo, wd, o, d);
+    rec.t = ch.t;
+    rec.material = op.z;
+    rec.prim_id = op.w;
+    rec.point = o + d * ch.t;
+    d3 outward;
+    if (op.x == OP_SPHERE) {
+        const SphereGeom g = S.spheres[op.y];
+        d3 center = mk(g.cx, g.cy, g.cz);
+        if (S.has_moving) {
+            const SphereAux ax = S.sphere_aux[op.y];
+            if (ax.is_moving) center = center + mk(ax.mx, ax.my, ax.mz) * time;
+        }
+        outward = (rec.point - center) / g.radius;
+        rec.is_sphere = 1;
+        rec.sphere_outward = outward;
+        rec.u = 0; rec.v = 0;
+        if (want_uv) sphere_uv(outward, rec.u, rec.v);
+    } else {
+        const QuadGeom q = S.quads[op.y];
+        d3 planar = rec.point - mk(q.sx, q.sy, q.sz);
+        rec.u = dot(mk(q.wx, q.wy, q.wz), cross(planar, mk(q.vx, q.vy, q.vz)));
+        rec.v = dot(mk(q.wx, q.wy, q.wz), cross(mk(q.ux, q.uy, q.uz), planar));
+        outward = mk(q.nx, q.ny, q.nz);
+        rec.is_sphere = 0;
+        rec.sphere_outward = outward;
+    }
+    rec.front_face = dot(d, outward) < 0.0;
+    rec.normal = rec.front_face ? outward : -outward;
+    for (uint32_t k = ch.xform; k != WRT_NONE; k = S.xforms[k].parent) {
+        const Xform X = S.xforms[k];
+        if (X.kind == OP_PUSH_TRANSLATE) {
+            rec.point = rec.point + mk(X.a, X.b, X.c);
+        } else {
+            const double sn = X.a, cs = X.b;
+            d3 p = rec.point, n = rec.normal;
+            rec.point = mk(cs * p.x + sn * p.z, p.y, -sn * p.x + cs * p.z);
+            rec.normal = mk(cs * n.x + sn * n.z, n.y, -sn * n.x + cs * n.z);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Textures (texture.zig)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool texture_needs_uv(const DeviceScene& S, uint32_t tex) {
+    const Texture T = S.textures[tex];
+    if (T.kind == WRT_TEX_IMAGE) return true;
+    if (T.kind == WRT_TEX_CHECKER) return S.textures[T.even].kind != WRT_TEX_SOLID || S.textures[T.odd].kind != WRT_TEX_SOLID;
+    return false;
+}
+
+__device__ inline d3 texture_value(const DeviceScene& S, uint32_t tex, double u, double v, d3 point) {
+    // checker textures nest (texture.zig:111-118); solid / image terminate.  Depth is bounded at upload.
+    for (int guard = 0; guard < 16; ++guard) {
+        const Texture T = S.textures[tex];
+        if (T.kind == WRT_TEX_SOLID) return mk(T.r, T.g, T.b);  // texture.zig:89-93
+        if (T.kind == WRT_TEX_CHECKER) {
+            int xi = (int)floor(T.inv_scale * point.x);
+            int yi = (int)floor(T.inv_scale * point.y);
+            int zi = (int)floor(T.inv_scale * point.z);
+            int m = (xi + yi + zi) % 2;
+            if (m < 0) m += 2;  // @mod
+            tex = (m == 0) ? T.even : T.odd;
+            continue;
+        }
+        // ImageTexture.value, texture.zig:49-68 + Image.getPixel, image.zig:23-36 + pixelToColor, texture.zig:70-77
+        const ImageDesc im = S.images[T.image];
+        double r, g, b;
+        if (im.height == 0) {
+            r = 255.0; g = 0.0; b = 255.0;  // ERR_COLOR, image.zig:5
+        } else {
+            double uu = clamp01(u);
+            double vv = 1.0 - clamp01(v);
+            unsigned long long xi = (unsigned long long)(uu * (double)im.width);
+            unsigned long long yi = (unsigned long long)(vv * (double)im.height);
+            uint32_t cx = xi > (unsigned long long)(im.width - 1) ? im.width - 1 : (uint32_t)xi;
+            uint32_t cy = yi > (unsigned long long)(im.height - 1) ? im.height - 1 : (uint32_t)yi;
+            uchar4 px = tex2D<uchar4>(im.tex, (float)cx + 0.5f, (float)cy + 0.5f);
+            r = (double)px.x; g = (double)px.y; b = (double)px.z;
+        }
+        const double scale = 1.0 / 255.0;
+        d3 c = mk(scale * r, scale * g, scale * b);
+        return c * c;  // linearizeColorSpace, math.zig:172-174
+    }
+    return mk(0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Light sampling hooks (entity.zig:371-386, 503-525, 626-651, 668-679) and PDFs (pdf.zig)
+// ---------------------------------------------------------------------------------------------------------
+__device__ inline double light_pdf_value_one(const DeviceScene& S, const Light L, d3 origin, d3 direction) {
+    if (L.kind == WRT_ENT_QUAD) {
+        const QuadGeom q = S.quads[L.index];
+        d3 n = mk(q.nx, q.ny, q.nz);
+        double denom = dot(n, direction);
+        if (fabs(denom) < 1e-8) return 0.0;
+        double t = (q.offset - dot(n, origin)) / denom;
+        if (!((1e-3 <= t) && (t <= CUDART_INF))) return 0.0;
+        d3 p = origin + direction * t;
+        d3 planar = p - mk(q.sx, q.sy, q.sz);
+        double alpha = dot(mk(q.wx, q.wy, q.wz), cross(planar, mk(q.vx, q.vy, q.vz)));
+        double beta = dot(mk(q.wx, q.wy, q.wz), cross(mk(q.ux, q.uy, q.uz), planar));
+        if (!((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0))) return 0.0;
+        // record.normal is the face-forwarded normal; only |dot| is used (entity.zig:515)
+        double dir_length_sq = dot(direction, direction);
+        double dist_sq = t * t * dir_length_sq;
+        bool front = dot(direction, n) < 0.0;
+        d3 nn = front ? n : -n;
+        double cosine = fabs(dot(direction, nn)) / sqrt(dir_length_sq);
+        return dist_sq / (cosine * q.area);
+    }
+    if (L.kind == WRT_ENT_SPHERE) {
+        const SphereGeom g = S.spheres[L.index];
+        d3 center = mk(g.cx, g.cy, g.cz);
+        d3 oc = center - origin;
+        double a = dot(direction, direction);
+        double h = dot(direction, oc);
+        double c = dot(oc, oc) - g.radius * g.radius;
+        double disc = h * h - a * c;
+        if (disc < 0.0) return 0.0;
+        double sq = sqrt(disc);
+        double root = (h - sq) / a;
+        if (!((1e-3 < root) && (root < CUDART_INF))) {
+            root = (h + sq) / a;
+            if (!((1e-3 < root) && (root < CUDART_INF))) return 0.0;
+        }
+        d3 diff = center - origin;
+        double dist_sq = dot(diff, diff);
+        double cos_theta_max = sqrt(1.0 - g.radius * g.radius / dist_sq);
+        double solid_angle = 2.0 * WRT_PI * (1.0 - cos_theta_max);
+        return 1.0 / solid_angle;
+    }
+    return 0.0;  // entity.zig:47-55
+}
+
+__device__ inline double lights_pdf_value(const DeviceScene& S, d3 origin, d3 direction) {  // entity.zig:371-378
+    const double weight = 1.0 / (double)S.n_lights;
+    double sum = 0.0;
+    for (uint32_t i = 0; i < S.n_lights; ++i) sum += weight * light_pdf_value_one(S, S.lights[i], origin, direction);
+    return sum;
+}
+
+__device__ inline d3 lights_sample_direction(const DeviceScene& S, Rng& rng, d3 origin) {  // entity.zig:381-386
+    const uint32_t idx = rng_pick(rng, S.n_lights);
+    const Light L = S.lights[idx];
+    if (L.kind == WRT_ENT_QUAD) {  // entity.zig:520-525
+        const QuadGeom q = S.quads[L.index];
+        double r1 = rng_float(rng);
+        d3 u = mk(q.ux, q.uy, q.uz) * r1;
+        double r2 = rng_float(rng);
+        d3 v = mk(q.vx, q.vy, q.vz) * r2;
+        d3 p = (mk(q.sx, q.sy, q.sz) + u) + v;
+        return p - origin;
+    }
+    if (L.kind == WRT_ENT_SPHERE) {  // entity.zig:646-651 + randomToSphere :668-679
+        const SphereGeom g = S.spheres[L.index];
+        d3 direction = mk(g.cx, g.cy, g.cz) - origin;
+        double dist_sq = dot(direction, direction);
+        Onb basis = onb_init(direction);
+        double r1 = rng_float(rng);
+        double r2 = rng_float(rng);
+        double z = 1.0 + r2 * (sqrt(1.0 - g.radius * g.radius / dist_sq) - 1.0);
+        double phi = 2.0 * WRT_PI * r1;
+        double sz2 = sqrt(1.0 - z * z);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        return onb_transform(basis, mk(cs * sz2, sn * sz2, z));
+    }
+    return mk(1, 0, 0);  // entity.zig:58-65
+}
+
+__device__ __forceinline__ d3 sample_cosine_direction_z(Rng& rng) {  // rng.zig:104-114
+    double r1 = rng_float(rng);
+    double r2 = rng_float(rng);
+    double phi = 2.0 * WRT_PI * r1;
+    double sn, cs;
+    sincos(phi, &sn, &cs);
+    double sr2 = sqrt(r2);
+    return mk(cs * sr2, sn * sr2, sqrt(1.0 - r2));
+}
+__device__ __forceinline__ d3 sample_unit_sphere(Rng& rng) {  // rng.zig:87-95 (direct form)
+    double u1 = rng_float(rng), u2 = rng_float(rng);
+    double z = 1.0 - 2.0 * u1;
+    double s = sqrt(fmax(0.0, 1.0 - z * z));
+    double phi = 2.0 * WRT_PI * u2;
+    double sn, cs;
+    sincos(phi, &sn, &cs);
+    return mk(cs * s, sn * s, z);
+}
+
+// writer.zig:68-94 encodeColor: NaN -> 0, sqrt, clamp [0, 0.999], * 256, truncate
+__device__ __forceinline__ uint8_t encode_channel(double c) {
+    if (c != c) c = 0.0;
+    c = sqrt(c);
+    c = fmax(0.0, fmin(c, 0.999));
+    return (uint8_t)(256.0 * c);
+}
+
+}  // namespace wrt

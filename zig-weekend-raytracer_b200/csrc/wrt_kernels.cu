@@ -1,0 +1,379 @@
+// wrt_kernels.cu — sm_100a kernels of the render back end.
+//
+//   render_kernel<CULL>      persistent warps pull (row, 32-column block, sample chunk) jobs — the reference's job
+//                            shape (render.zig:55-73) times a sample split — and run the iterative form of rayColor
+//                            (render.zig:188-289).  Each lane owns one pixel of the block and
+//                            regenerates a new camera sample as soon as its path ends, so lanes never idle while
+//                            the pixel still has samples; per-(pixel, chunk) sums go to a private slot.
+//   resolve_kernel           fused final pass: clear colour + ordered sum of the chunk slots -> caller's f64
+//                            framebuffer layout, and encodeColor (writer.zig:68-94) into RGB8.
+//   primary_hits_kernel / trace_rays_kernel / sobol_*_kernel   gates and diagnostics (include/wrt.h).
+#include <math_constants.h>
+
+#include "wrt_device.cuh"
+#include "wrt_kernels.h"
+
+namespace wrt {
+
+__constant__ SobolTables c_sobol;
+__constant__ RenderConstants c_rc;
+
+cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream) {
+    return cudaMemcpyToSymbolAsync(c_sobol, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
+}
+cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream) {
+    return cudaMemcpyToSymbolAsync(c_rc, &rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
+}
+
+__device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+// sampleRay, render.zig:144-174 (+ sampleDefocusDisk :182-185, rng.sampleUnitDiskXY rng.zig:76-78)
+__device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, bool dof, Rng* rng) {
+    uint64_t idx = sobol_interval_to_index(c_sobol, s, col, row);
+    double ox, oy;
+    sobol_pixel_2d(c_sobol, idx, col, row, ox, oy);
+    d3 sample = (ld3(rc.cam.pixel00_loc) + ld3(rc.cam.pixel_delta_u) * ((double)col + ox)) +
+                ld3(rc.cam.pixel_delta_v) * ((double)row + oy);
+    d3 origin = ld3(rc.cam.position);
+    if (dof) {
+        double rr = 1.0 * rng_float(*rng);  // radius * float, evaluated before the circle sample
+        double phi = 2.0 * WRT_PI * rng_float(*rng);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        d3 p = mk(cs, sn, 0.0) * rr;
+        origin = (ld3(rc.cam.position) + ld3(rc.cam.defocus_disk_u) * p.x) + ld3(rc.cam.defocus_disk_v) * p.y;
+    }
+    Ray r;
+    r.o = origin;
+    r.d = sample - origin;
+    r.time = 0.0;
+    if (rng) {
+        // time = rand.float (render.zig:167): the draw is always consumed; the value only matters for moving spheres
+        r.time = rng_float(*rng);
+    }
+    return r;
+}
+
+// material.zig:221-225 (x^5 by multiplication instead of std.math.pow)
+__device__ __forceinline__ double reflectance(double ir, double cosine) {
+    double r0 = (1 - ir) / (1 + ir);
+    r0 *= r0;
+    double x = 1 - cosine;
+    double x2 = x * x;
+    return r0 + (1 - r0) * (x2 * x2 * x);
+}
+
+// One bounce of rayColor in throughput form.  Returns false when the path ends.
+//   L    += beta * emitted                     (render.zig:234,288)
+//   beta *= attenuation [* scatteringPdf/pdf]  (render.zig:245, 282-285)
+template <int CULL>
+__device__ __forceinline__ bool path_step(const DeviceScene& S, const RenderConstants& rc, Ray& ray, d3& beta, d3& L, Rng& rng,
+                                          unsigned long long& n_rays) {
+    ++n_rays;
+    const ClosestHit ch = closest_hit<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+    if (ch.pc == WRT_NONE) {  // render.zig:215-217
+        L = L + beta * ld3(rc.background);
+        return false;
+    }
+    const uint32_t mat_id = __ldg(&S.ops[ch.pc].z);
+    const Material M = S.materials[mat_id];
+    const bool textured = (M.kind == WRT_MAT_LAMBERTIAN || M.kind == WRT_MAT_ISOTROPIC || M.kind == WRT_MAT_DIFFUSE_EMISSIVE);
+    const bool want_uv = textured && texture_needs_uv(S, M.texture);
+    HitRecord rec;
+    resolve_hit(S, ch, ray.o, ray.d, ray.time, want_uv, rec);
+
+    if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) {  // material.zig:88-96; no scatter => return emission (render.zig:238-240)
+        // back faces emit 0; the product is still formed so that a NaN/inf throughput poisons the sample as it does
+        // in the reference's recursion (0 * NaN), which the writer later zeroes (writer.zig:72-94)
+        d3 e = rec.front_face ? texture_value(S, M.texture, rec.u, rec.v, rec.point) : mk(0, 0, 0);
+        L = L + beta * e;
+        return false;
+    }
+    if (M.kind == WRT_MAT_METAL) {  // material.zig:163-178
+        double blur = clamp01(M.param);
+        d3 refl = reflect(ray.d, rec.normal);
+        d3 dir = refl + sample_unit_sphere(rng) * blur;
+        if (!(dot(dir, rec.normal) > 0.0)) {  // scatter false => emission (0)
+            L = L + beta * 0.0;
+            return false;
+        }
+        beta = beta * mk(M.ar, M.ag, M.ab);
+        ray.o = rec.point;
+        ray.d = dir;
+        return true;
+    }
+    if (M.kind == WRT_MAT_DIELECTRIC) {  // material.zig:190-218
+        double index = rec.front_face ? 1.0 / M.param : M.param;
+        d3 in_unit = normalize(ray.d);
+        double cos_theta = fmin(dot(-in_unit, rec.normal), 1.0);
+        double sin_theta = sqrt(1 - cos_theta * cos_theta);
+        d3 dir;
+        if (index * sin_theta > 1.0 || reflectance(M.param, cos_theta) > rng_float(rng)) dir = reflect(in_unit, rec.normal);
+        else dir = refract(in_unit, rec.normal, index);
+        ray.o = rec.point;  // attenuation (1,1,1)
+        ray.d = dir;
+        return true;
+    }
+    // lambertian / isotropic: importance-sampled diffuse bounce (render.zig:248-288)
+    const d3 attenuation = texture_value(S, M.texture, rec.u, rec.v, rec.point);
+    const bool cosine_pdf = (M.kind == WRT_MAT_LAMBERTIAN) || !S.has_lights;  // render.zig:264-269 forces cosine without lights
+    Onb basis;
+    if (cosine_pdf) basis = onb_init(rec.normal);
+    d3 dir;
+    double pdf_value;
+    if (S.has_lights) {  // MixturePdf(EntityPdf(lights), material pdf), pdf.zig:99-118
+        double p = rng_float(rng);
+        if (p < 0.5) dir = lights_sample_direction(S, rng, rec.point);
+        else dir = cosine_pdf ? onb_transform(basis, sample_cosine_direction_z(rng)) : sample_unit_sphere(rng);
+        double p1 = lights_pdf_value(S, rec.point, dir);
+        double p2 = cosine_pdf ? fmax(0.0, dot(normalize(dir), basis.w) / WRT_PI) : 1.0 / (4.0 * WRT_PI);
+        pdf_value = 0.5 * p1 + 0.5 * p2;
+    } else {
+        dir = onb_transform(basis, sample_cosine_direction_z(rng));
+        pdf_value = fmax(0.0, dot(normalize(dir), basis.w) / WRT_PI);
+    }
+    double sp;  // material.scatteringPdf, material.zig:118-125 / 145-150
+    if (M.kind == WRT_MAT_LAMBERTIAN) sp = fmax(0.0, dot(rec.normal, normalize(dir)) / WRT_PI);
+    else sp = 1.0 / (4.0 * WRT_PI);
+    beta = (beta * (attenuation * sp)) / pdf_value;
+    ray.o = rec.point;
+    ray.d = dir;
+    return true;
+}
+
+template <int CULL>
+__global__ void __launch_bounds__(WRT_RENDER_BLOCK) render_kernel(DeviceScene S, double* __restrict__ accum,
+                                                                  unsigned long long* __restrict__ counters) {
+    const RenderConstants& rc = c_rc;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long n_rays = 0, n_paths = 0;
+    const double scale = 1.0 / (double)rc.spp;  // pixel_color_scale, render.zig:123
+    const bool dof = rc.dof != 0;
+    const uint32_t k0 = (uint32_t)rc.seed, k1 = (uint32_t)(rc.seed >> 32);
+
+    for (;;) {
+        unsigned long long job = 0;
+        if (lane == 0) job = atomicAdd(&counters[0], 1ull);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= rc.total_jobs) break;
+        // job -> (chunk, local row, column block); chunks outermost so that late jobs are the short ones
+        const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
+        const uint32_t chunk = (uint32_t)(job / blocks_per_chunk);
+        const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
+        const uint32_t local_row = rem / rc.n_col_blocks;
+        const uint32_t col = (rem % rc.n_col_blocks) * 32u + lane;
+        const uint32_t row = rc.row_shard_index + local_row * rc.row_shard_count;
+        const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
+        const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
+        const bool lane_active = col < rc.width;
+
+        d3 color = mk(0, 0, 0);
+        uint32_t s = s_first;
+        bool alive = false;
+        uint32_t depth_left = 0;
+        Ray ray;
+        d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
+        Rng rng;
+        rng.k0 = k0; rng.k1 = k1; rng.pixel = row * rc.width + col; rng.sample = 0; rng.draw = 0;
+
+        for (;;) {
+            if (!alive && lane_active && s < s_last) {
+                rng.sample = s; rng.draw = 0;
+                ray = sample_ray(rc, col, row, s, dof, &rng);
+                beta = mk(1, 1, 1); L = mk(0, 0, 0);
+                depth_left = rc.max_depth;
+                alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
+                ++n_paths;
+                if (!alive) ++s;
+            }
+            if (!__any_sync(0xffffffffu, alive)) {
+                if (!__any_sync(0xffffffffu, lane_active && s < s_last)) break;
+                continue;
+            }
+            if (alive) {
+                bool cont = path_step<CULL>(S, rc, ray, beta, L, rng, n_rays);
+                --depth_left;
+                if (!cont || depth_left == 0) {
+                    if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
+                    color = color + L * scale;  // render.zig:129-135
+                    alive = false;
+                    ++s;
+                }
+            }
+        }
+        if (lane_active) {
+            double* slot = accum + ((size_t)chunk * rc.n_rows_local * rc.width + (size_t)local_row * rc.width + col) * 3;
+            slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
+        }
+    }
+    // ray / path accounting: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
+        n_paths += __shfl_down_sync(0xffffffffu, n_paths, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[1], n_rays);
+        atomicAdd(&counters[2], n_paths);
+    }
+}
+
+// Final pass: framebuffer[pixel] = (clear | previous contents) + sum over chunks in order; optional RGB8.
+__global__ void resolve_kernel(const double* __restrict__ accum, uint32_t n_chunks, uint32_t n_pixels, double clear_r,
+                               double clear_g, double clear_b, int no_clear, double* __restrict__ fb, uint32_t stride_doubles,
+                               uint8_t* __restrict__ rgb8) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    double* px = fb + (size_t)i * stride_doubles;
+    double r = no_clear ? px[0] : clear_r, g = no_clear ? px[1] : clear_g, b = no_clear ? px[2] : clear_b;
+    d3 sum = mk(0, 0, 0);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const double* slot = accum + ((size_t)c * n_pixels + i) * 3;
+        sum = sum + mk(slot[0], slot[1], slot[2]);
+    }
+    r += sum.x; g += sum.y; b += sum.z;  // framebuffer.buffer[..] += color, render.zig:139
+    px[0] = r; px[1] = g; px[2] = b;
+    for (uint32_t k = 3; k < stride_doubles; ++k) px[k] = 0.0;
+    if (rgb8) {
+        rgb8[3 * (size_t)i + 0] = encode_channel(r);
+        rgb8[3 * (size_t)i + 1] = encode_channel(g);
+        rgb8[3 * (size_t)i + 2] = encode_channel(b);
+    }
+}
+
+__global__ void encode_kernel(const double* __restrict__ fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* __restrict__ rgb8) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const double* px = fb + (size_t)i * stride_doubles;
+    rgb8[3 * (size_t)i + 0] = encode_channel(px[0]);
+    rgb8[3 * (size_t)i + 1] = encode_channel(px[1]);
+    rgb8[3 * (size_t)i + 2] = encode_channel(px[2]);
+}
+
+template <int CULL>
+__global__ void primary_hits_kernel(DeviceScene S, uint32_t n_samples, uint32_t* __restrict__ ids, double* __restrict__ ts) {
+    const RenderConstants& rc = c_rc;
+    const uint64_t total = (uint64_t)rc.width * rc.height * n_samples;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t s = (uint32_t)(i % n_samples);
+        uint64_t pix = i / n_samples;
+        uint32_t col = (uint32_t)(pix % rc.width), row = (uint32_t)(pix / rc.width);
+        Ray r = sample_ray(rc, col, row, s, false, nullptr);
+        ClosestHit ch = closest_hit<CULL>(S, r.o, r.d, 0.0, 1e-4, CUDART_INF);
+        if (ids) ids[i] = (ch.pc == WRT_NONE) ? WRT_NONE : __ldg(&S.ops[ch.pc].w);
+        if (ts) ts[i] = (ch.pc == WRT_NONE) ? CUDART_INF : ch.t;
+    }
+}
+
+template <int CULL>
+__global__ void trace_rays_kernel(DeviceScene S, const double* __restrict__ origins, const double* __restrict__ dirs, uint64_t n,
+                                  double tmin, uint32_t* ids, double* ts, double* point, double* normal, double* uv,
+                                  uint32_t* front_face) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        d3 o = ld3(origins + 3 * i), d = ld3(dirs + 3 * i);
+        ClosestHit ch = closest_hit<CULL>(S, o, d, 0.0, tmin, CUDART_INF);
+        const bool hit = ch.pc != WRT_NONE;
+        HitRecord rec;
+        if (hit) resolve_hit(S, ch, o, d, 0.0, true, rec);
+        if (ids) ids[i] = hit ? rec.prim_id : WRT_NONE;
+        if (ts) ts[i] = hit ? rec.t : CUDART_INF;
+        if (point) { point[3 * i] = hit ? rec.point.x : 0; point[3 * i + 1] = hit ? rec.point.y : 0; point[3 * i + 2] = hit ? rec.point.z : 0; }
+        if (normal) { normal[3 * i] = hit ? rec.normal.x : 0; normal[3 * i + 1] = hit ? rec.normal.y : 0; normal[3 * i + 2] = hit ? rec.normal.z : 0; }
+        if (uv) { uv[2 * i] = hit ? rec.u : 0; uv[2 * i + 1] = hit ? rec.v : 0; }
+        if (front_face) front_face[i] = hit ? rec.front_face : 0;
+    }
+}
+
+__global__ void sobol_pixel_kernel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+                                   double* offsets) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t idx = sobol_interval_to_index(c_sobol, sidx[i], cols[i], rows[i]);
+        if (index_out) index_out[i] = idx;
+        if (offsets) sobol_pixel_2d(c_sobol, idx, cols[i], rows[i], offsets[2 * i], offsets[2 * i + 1]);
+    }
+}
+
+// sampleDimension (sampler.zig:236-247) over the full 1024 x 52 table in global memory
+__global__ void sobol_dimension_kernel(const uint32_t* __restrict__ matrices, const uint64_t* index, const uint32_t* dimension,
+                                       uint64_t n, uint32_t owen_fast, uint32_t seed, float* out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t a = index[i];
+        uint32_t dim = dimension[i];
+        uint32_t v = 0;
+        for (uint32_t k = dim * 52u; a != 0; a >>= 1, ++k)
+            if (a & 1) v ^= __ldg(matrices + k);
+        if (owen_fast) v = owen_fast_apply(murmur2_u32(dim, seed), v);
+        out[i] = sobol_sample_bits_to_float(v);
+    }
+}
+
+// FP64 issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for the issue-bound configs,
+// BASELINE.md §4).  The result is stored so the chains cannot be optimised away.
+__global__ void fp64_peak_kernel(double* out, uint32_t iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (uint32_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream) {
+    fp64_peak_kernel<<<grid, block, 0, stream>>>(out, iters, 0.5);
+    return cudaGetLastError();
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+                          cudaStream_t stream) {
+    if (cull_mode == WRT_CULL_REFERENCE) render_kernel<WRT_CULL_REFERENCE><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+    else render_kernel<WRT_CULL_TIGHT><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+    return cudaGetLastError();
+}
+cudaError_t render_occupancy(uint32_t cull_mode, int* blocks_per_sm) {
+    if (cull_mode == WRT_CULL_REFERENCE)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<WRT_CULL_REFERENCE>, WRT_RENDER_BLOCK, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<WRT_CULL_TIGHT>, WRT_RENDER_BLOCK, 0);
+}
+cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
+                           uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(accum, n_chunks, n_pixels, clear[0], clear[1], clear[2], no_clear, fb,
+                                                                 stride_doubles, rgb8);
+    return cudaGetLastError();
+}
+cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* rgb8, cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    encode_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(fb, stride_doubles, n_pixels, rgb8);
+    return cudaGetLastError();
+}
+cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
+                                cudaStream_t stream) {
+    if (cull_mode == WRT_CULL_REFERENCE) primary_hits_kernel<WRT_CULL_REFERENCE><<<grid, 128, 0, stream>>>(S, n_samples, ids, ts);
+    else primary_hits_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(S, n_samples, ids, ts);
+    return cudaGetLastError();
+}
+cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, const double* origins, const double* dirs, uint64_t n, double tmin,
+                              uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face, uint32_t grid,
+                              cudaStream_t stream) {
+    if (cull_mode == WRT_CULL_REFERENCE)
+        trace_rays_kernel<WRT_CULL_REFERENCE><<<grid, 128, 0, stream>>>(S, origins, dirs, n, tmin, ids, ts, point, normal, uv, front_face);
+    else
+        trace_rays_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(S, origins, dirs, n, tmin, ids, ts, point, normal, uv, front_face);
+    return cudaGetLastError();
+}
+cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+                               double* offsets, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = (uint32_t)((n + 127) / 128 < 4096 ? (n + 127) / 128 : 4096);
+    sobol_pixel_kernel<<<grid, 128, 0, stream>>>(cols, rows, sidx, n, index_out, offsets);
+    return cudaGetLastError();
+}
+cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
+                                   uint32_t owen_fast, uint32_t seed, float* out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = (uint32_t)((n + 127) / 128 < 4096 ? (n + 127) / 128 : 4096);
+    sobol_dimension_kernel<<<grid, 128, 0, stream>>>(matrices, index, dimension, n, owen_fast, seed, out);
+    return cudaGetLastError();
+}
+
+}  // namespace wrt

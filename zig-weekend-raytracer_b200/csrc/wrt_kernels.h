@@ -1,0 +1,49 @@
+// wrt_kernels.h — host-visible interface of wrt_kernels.cu (launchers + constant blocks).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wrt.h"
+
+#define WRT_RENDER_BLOCK 128
+
+namespace wrt {
+
+struct DeviceScene;
+struct SobolTables;
+
+// Per-render constants (one __constant__ block): the RenderThreadContext of the reference (render.zig:78-103)
+// plus the job decomposition.
+struct RenderConstants {
+    wrt_camera cam;
+    double background[3];
+    unsigned long long seed;
+    unsigned long long total_jobs;  // n_chunks * n_rows_local * n_col_blocks
+    uint32_t width, height, spp, max_depth, dof;
+    uint32_t row_shard_index, row_shard_count, n_rows_local, n_col_blocks;
+    uint32_t sample_begin, sample_end, chunk_size, n_chunks;
+};
+
+cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream);
+cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream);
+
+cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+                          cudaStream_t stream);
+cudaError_t render_occupancy(uint32_t cull_mode, int* blocks_per_sm);
+cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
+                           uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream);
+cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* rgb8, cudaStream_t stream);
+cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
+                                cudaStream_t stream);
+cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, const double* origins, const double* dirs, uint64_t n, double tmin,
+                              uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face, uint32_t grid,
+                              cudaStream_t stream);
+cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+                               double* offsets, cudaStream_t stream);
+cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
+                                   uint32_t owen_fast, uint32_t seed, float* out, cudaStream_t stream);
+
+cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream);
+
+}  // namespace wrt

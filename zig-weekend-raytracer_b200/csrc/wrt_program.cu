@@ -1,0 +1,368 @@
+// wrt_program.cu — host code only (compiled by nvcc for the shared struct definitions).
+//
+// Turns the reference's pointer tree (IEntity, src/entity.zig:17-24, passed as wrt_entity records) into
+//   * a linear program in DFS pre-order — exactly the order BVHNodeEntity.hit / EntityCollection.hit visit
+//     children (entity.zig:286-303, 342-368) — where every bvh_node carries the pc to jump to when culled;
+//   * two box sets per node: the reference's own cached box (for WRT_CULL_REFERENCE) and a conservative box
+//     recomputed from the primitives in the node's local space (for WRT_CULL_TIGHT);
+//   * primitive ids = first-visit DFS order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "wrt_program.h"
+
+namespace wrt {
+namespace {
+
+struct Box3 {
+    double mn[3], mx[3];
+    void reset() {
+        for (int k = 0; k < 3; ++k) { mn[k] = std::numeric_limits<double>::infinity(); mx[k] = -std::numeric_limits<double>::infinity(); }
+    }
+    void grow(const double p[3]) {
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], p[k]); mx[k] = std::max(mx[k], p[k]); }
+    }
+    void grow(const Box3& b) {
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], b.mn[k]); mx[k] = std::max(mx[k], b.mx[k]); }
+    }
+    bool valid() const { return mn[0] <= mx[0]; }
+};
+
+struct Compiler {
+    const wrt_scene* sc;
+    CompiledScene& out;
+    std::string& err;
+    int code = WRT_OK;
+
+    std::vector<Box3> tight;          // per entity, local space; valid flag in tight_state
+    std::vector<uint8_t> tight_state; // 0 = not computed, 1 = in progress, 2 = done
+    std::vector<uint32_t> prim_id;    // per entity (sphere / quad), WRT_NONE until first visit
+    std::vector<uint8_t> on_stack;    // cycle guard for emit()
+
+    Compiler(const wrt_scene* s, CompiledScene& o, std::string& e) : sc(s), out(o), err(e) {}
+
+    bool fail(int c, const std::string& msg) {
+        if (code == WRT_OK) { code = c; err = msg; }
+        return false;
+    }
+
+    bool check_entity(uint32_t id, const char* what) {
+        if (id >= sc->n_entities) return fail(WRT_E_INVALID, std::string("entity index out of range in ") + what);
+        return true;
+    }
+
+    // ---- conservative local-space boxes ---------------------------------------------------------------
+    bool tight_box(uint32_t id, Box3& b) {
+        if (!check_entity(id, "tight_box")) return false;
+        if (tight_state[id] == 2) { b = tight[id]; return true; }
+        if (tight_state[id] == 1) return fail(WRT_E_INVALID, "entity graph contains a cycle");
+        tight_state[id] = 1;
+        const wrt_entity& e = sc->entities[id];
+        b.reset();
+        switch (e.kind) {
+            case WRT_ENT_SPHERE: {
+                if (e.a >= sc->n_spheres) return fail(WRT_E_INVALID, "sphere index out of range");
+                const wrt_sphere& s = sc->spheres[e.a];
+                const double r = std::fabs(s.radius);
+                double lo[3], hi[3];
+                for (int k = 0; k < 3; ++k) { lo[k] = s.center[k] - r; hi[k] = s.center[k] + r; }
+                b.grow(lo); b.grow(hi);
+                if (s.is_moving) {
+                    for (int k = 0; k < 3; ++k) { lo[k] += s.movement[k]; hi[k] += s.movement[k]; }
+                    b.grow(lo); b.grow(hi);
+                }
+                break;
+            }
+            case WRT_ENT_QUAD: {
+                if (e.a >= sc->n_quads) return fail(WRT_E_INVALID, "quad index out of range");
+                const wrt_quad& q = sc->quads[e.a];
+                for (int i = 0; i < 2; ++i)
+                    for (int j = 0; j < 2; ++j) {
+                        double p[3];
+                        for (int k = 0; k < 3; ++k) p[k] = q.start[k] + i * q.u[k] + j * q.v[k];
+                        b.grow(p);
+                    }
+                break;
+            }
+            case WRT_ENT_COLLECTION: {
+                if ((uint64_t)e.a + e.b > sc->n_children && e.b) return fail(WRT_E_INVALID, "collection child range out of bounds");
+                for (uint32_t k = 0; k < e.b; ++k) {
+                    Box3 cb;
+                    if (!tight_box(sc->children[e.a + k], cb)) return false;
+                    if (cb.valid()) b.grow(cb);
+                }
+                break;
+            }
+            case WRT_ENT_BVH_NODE: {
+                Box3 l, r;
+                if (!tight_box(e.a, l) || !tight_box(e.b, r)) return false;
+                if (l.valid()) b.grow(l);
+                if (r.valid()) b.grow(r);
+                break;
+            }
+            case WRT_ENT_TRANSLATE: {
+                Box3 c;
+                if (!tight_box(e.a, c)) return false;
+                if (c.valid())
+                    for (int k = 0; k < 3; ++k) { b.mn[k] = c.mn[k] + e.p[k]; b.mx[k] = c.mx[k] + e.p[k]; }
+                break;
+            }
+            case WRT_ENT_ROTATE_Y: {
+                Box3 c;
+                if (!tight_box(e.a, c)) return false;
+                if (c.valid()) {
+                    const double sn = e.p[0], cs = e.p[1];
+                    for (int i = 0; i < 2; ++i)
+                        for (int j = 0; j < 2; ++j)
+                            for (int k = 0; k < 2; ++k) {
+                                const double x = i ? c.mx[0] : c.mn[0], y = j ? c.mx[1] : c.mn[1], z = k ? c.mx[2] : c.mn[2];
+                                double p[3] = {cs * x + sn * z, y, -sn * x + cs * z};  // objectToWorldSpace, entity.zig:199-205
+                                b.grow(p);
+                            }
+                }
+                break;
+            }
+            default: return fail(WRT_E_INVALID, "unknown entity kind");
+        }
+        tight[id] = b;
+        tight_state[id] = 2;
+        return true;
+    }
+
+    static BoxTight padded(const Box3& b) {
+        BoxTight t;
+        if (!b.valid()) {  // empty subtree: a box nothing can hit
+            t.x = make_double2(1.0, -1.0); t.y = t.x; t.z = t.x;
+            return t;
+        }
+        double mag = 1.0;
+        for (int k = 0; k < 3; ++k) mag = std::max(mag, std::max(std::fabs(b.mn[k]), std::fabs(b.mx[k])));
+        const double pad = mag * 1e-7;  // >> binary64 rounding of the slab arithmetic, << any scene feature
+        t.x = make_double2(b.mn[0] - pad, b.mx[0] + pad);
+        t.y = make_double2(b.mn[1] - pad, b.mx[1] + pad);
+        t.z = make_double2(b.mn[2] - pad, b.mx[2] + pad);
+        return t;
+    }
+
+    uint32_t push_box(const wrt_entity& e, const Box3& tb) {
+        BoxRef r;
+        r.min_x = e.bbox_min[0]; r.min_y = e.bbox_min[1];
+        r.max_x = e.bbox_max[0]; r.max_y = e.bbox_max[1];
+        out.boxes_ref.push_back(r);
+        out.boxes_tight.push_back(padded(tb));
+        return (uint32_t)(out.boxes_ref.size() - 1);
+    }
+
+    // ---- program emission ------------------------------------------------------------------------------
+    bool emit(uint32_t id, uint32_t xf, uint32_t xf_depth) {
+        if (!check_entity(id, "emit")) return false;
+        if (on_stack[id]) return fail(WRT_E_INVALID, "entity graph contains a cycle");
+        on_stack[id] = 1;
+        const wrt_entity& e = sc->entities[id];
+        bool ok = true;
+        switch (e.kind) {
+            case WRT_ENT_SPHERE:
+            case WRT_ENT_QUAD: {
+                const bool sphere = e.kind == WRT_ENT_SPHERE;
+                if (e.a >= (sphere ? sc->n_spheres : sc->n_quads)) { ok = fail(WRT_E_INVALID, "primitive index out of range"); break; }
+                const uint32_t mat = sphere ? sc->spheres[e.a].material : sc->quads[e.a].material;
+                if (mat >= sc->n_materials) { ok = fail(WRT_E_INVALID, "material index out of range"); break; }
+                if (prim_id[id] == WRT_NONE) prim_id[id] = out.n_prims++;
+                out.ops.push_back(make_uint4(sphere ? OP_SPHERE : OP_QUAD, e.a, mat, prim_id[id]));
+                break;
+            }
+            case WRT_ENT_COLLECTION: {
+                if (e.c != WRT_NONE) { ok = emit(e.c, xf, xf_depth); break; }  // prefer the BVH (entity.zig:347-349)
+                if ((uint64_t)e.a + e.b > sc->n_children && e.b) { ok = fail(WRT_E_INVALID, "collection child range out of bounds"); break; }
+                for (uint32_t k = 0; k < e.b && ok; ++k) ok = emit(sc->children[e.a + k], xf, xf_depth);
+                break;
+            }
+            case WRT_ENT_BVH_NODE: {
+                Box3 tb;
+                if (!tight_box(id, tb)) { ok = false; break; }
+                const uint32_t box = push_box(e, tb);
+                const size_t at = out.ops.size();
+                out.ops.push_back(make_uint4(OP_NODE, box, 0, 0));
+                ok = emit(e.a, xf, xf_depth);
+                // span == 1 nodes hold the same child twice (entity.zig:231-233); the second visit cannot change the result
+                if (ok && e.b != e.a) ok = emit(e.b, xf, xf_depth);
+                out.ops[at].z = (uint32_t)out.ops.size();
+                break;
+            }
+            case WRT_ENT_TRANSLATE:
+            case WRT_ENT_ROTATE_Y: {
+                if (xf_depth + 1 > WRT_MAX_XFORM_DEPTH) { ok = fail(WRT_E_LIMIT, "transform nesting deeper than WRT_MAX_XFORM_DEPTH"); break; }
+                Box3 tb;
+                if (!tight_box(id, tb)) { ok = false; break; }
+                // compiler-inserted bound of the instance in its parent's space (ignored by reference culling)
+                const uint32_t box = push_box(e, tb);
+                const size_t at = out.ops.size();
+                out.ops.push_back(make_uint4(OP_NODE_TIGHT_ONLY, box, 0, 0));
+                Xform X;
+                X.parent = xf;
+                if (e.kind == WRT_ENT_TRANSLATE) { X.kind = OP_PUSH_TRANSLATE; X.a = e.p[0]; X.b = e.p[1]; X.c = e.p[2]; }
+                else { X.kind = OP_PUSH_ROTATE_Y; X.a = e.p[0]; X.b = e.p[1]; X.c = 0.0; }
+                out.xforms.push_back(X);
+                const uint32_t me = (uint32_t)(out.xforms.size() - 1);
+                out.max_xform_depth = std::max(out.max_xform_depth, xf_depth + 1);
+                out.ops.push_back(make_uint4(X.kind, me, 0, 0));
+                ok = emit(e.a, me, xf_depth + 1);
+                out.ops.push_back(make_uint4(OP_POP, xf, 0, 0));
+                out.ops[at].z = (uint32_t)out.ops.size();
+                break;
+            }
+            default: ok = fail(WRT_E_INVALID, "unknown entity kind");
+        }
+        on_stack[id] = 0;
+        return ok;
+    }
+
+    bool compile_materials() {
+        out.textures.resize(sc->n_textures);
+        for (uint32_t i = 0; i < sc->n_textures; ++i) {
+            const wrt_texture& t = sc->textures[i];
+            Texture T;
+            T.r = t.color[0]; T.g = t.color[1]; T.b = t.color[2]; T.inv_scale = t.inv_scale;
+            T.kind = t.kind; T.even = t.even; T.odd = t.odd; T.image = t.image;
+            if (t.kind == WRT_TEX_CHECKER && (t.even >= sc->n_textures || t.odd >= sc->n_textures))
+                return fail(WRT_E_INVALID, "checker texture child out of range");
+            if (t.kind == WRT_TEX_IMAGE && t.image >= sc->n_images) return fail(WRT_E_INVALID, "image index out of range");
+            if (t.kind > WRT_TEX_IMAGE) return fail(WRT_E_INVALID, "unknown texture kind");
+            out.textures[i] = T;
+        }
+        // checker nesting must terminate within the device loop bound
+        for (uint32_t i = 0; i < sc->n_textures; ++i) {
+            std::vector<uint32_t> stack{i};
+            std::vector<uint32_t> depth{0};
+            while (!stack.empty()) {
+                uint32_t t = stack.back(), d = depth.back();
+                stack.pop_back(); depth.pop_back();
+                if (d > 15) return fail(WRT_E_LIMIT, "checker textures nested deeper than 15 (or cyclic)");
+                if (sc->textures[t].kind == WRT_TEX_CHECKER) {
+                    stack.push_back(sc->textures[t].even); depth.push_back(d + 1);
+                    stack.push_back(sc->textures[t].odd); depth.push_back(d + 1);
+                }
+            }
+        }
+        out.materials.resize(sc->n_materials);
+        for (uint32_t i = 0; i < sc->n_materials; ++i) {
+            const wrt_material& m = sc->materials[i];
+            Material M;
+            M.ar = m.albedo[0]; M.ag = m.albedo[1]; M.ab = m.albedo[2]; M.param = m.param;
+            M.kind = m.kind; M.texture = m.texture; M._p0 = M._p1 = 0;
+            if (m.kind > WRT_MAT_DIFFUSE_EMISSIVE) return fail(WRT_E_INVALID, "unknown material kind");
+            const bool textured = m.kind == WRT_MAT_LAMBERTIAN || m.kind == WRT_MAT_ISOTROPIC || m.kind == WRT_MAT_DIFFUSE_EMISSIVE;
+            if (textured && m.texture >= sc->n_textures) return fail(WRT_E_INVALID, "material texture index out of range");
+            out.materials[i] = M;
+        }
+        return true;
+    }
+
+    bool compile_geometry() {
+        out.spheres.resize(sc->n_spheres);
+        for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+            const wrt_sphere& s = sc->spheres[i];
+            SphereGeom g;
+            g.cx = s.center[0]; g.cy = s.center[1]; g.cz = s.center[2]; g.radius = s.radius;
+            out.spheres[i] = g;
+            if (s.is_moving) out.has_moving = true;
+        }
+        if (out.has_moving) {
+            out.sphere_aux.resize(sc->n_spheres);
+            for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+                const wrt_sphere& s = sc->spheres[i];
+                SphereAux a;
+                a.mx = s.movement[0]; a.my = s.movement[1]; a.mz = s.movement[2];
+                a.is_moving = s.is_moving; a._pad = 0;
+                out.sphere_aux[i] = a;
+            }
+        }
+        out.quads.resize(sc->n_quads);
+        for (uint32_t i = 0; i < sc->n_quads; ++i) {
+            const wrt_quad& q = sc->quads[i];
+            QuadGeom g;
+            g.nx = q.normal[0]; g.ny = q.normal[1]; g.nz = q.normal[2]; g.offset = q.offset;
+            g.sx = q.start[0]; g.sy = q.start[1]; g.sz = q.start[2]; g.area = q.area;
+            g.ux = q.u[0]; g.uy = q.u[1]; g.uz = q.u[2]; g._p0 = 0;
+            g.vx = q.v[0]; g.vy = q.v[1]; g.vz = q.v[2]; g._p1 = 0;
+            g.wx = q.w[0]; g.wy = q.w[1]; g.wz = q.w[2]; g._p2 = 0;
+            out.quads[i] = g;
+        }
+        return true;
+    }
+
+    bool compile_lights() {
+        out.has_lights = false;
+        if (sc->lights == WRT_NONE) return true;
+        if (!check_entity(sc->lights, "lights")) return false;
+        const wrt_entity& L = sc->entities[sc->lights];
+        auto add = [&](uint32_t id) -> bool {
+            if (!check_entity(id, "lights child")) return false;
+            const wrt_entity& e = sc->entities[id];
+            Light l;
+            l.index = 0;
+            if (e.kind == WRT_ENT_SPHERE) {
+                if (e.a >= sc->n_spheres) return fail(WRT_E_INVALID, "light sphere index out of range");
+                if (sc->spheres[e.a].is_moving) return fail(WRT_E_INVALID, "moving spheres cannot be lights (entity.zig:627 asserts)");
+                l.kind = WRT_ENT_SPHERE; l.index = e.a;
+            } else if (e.kind == WRT_ENT_QUAD) {
+                if (e.a >= sc->n_quads) return fail(WRT_E_INVALID, "light quad index out of range");
+                l.kind = WRT_ENT_QUAD; l.index = e.a;
+            } else if (e.kind == WRT_ENT_COLLECTION) {
+                return fail(WRT_E_LIMIT, "nested light collections are not supported");
+            } else {
+                l.kind = e.kind;  // pdfValue 0, direction (1,0,0): entity.zig:47-65
+            }
+            out.lights.push_back(l);
+            return true;
+        };
+        if (L.kind == WRT_ENT_COLLECTION) {
+            if (L.b == 0) return fail(WRT_E_INVALID, "light collection is empty (entity.zig:382 asserts len > 0)");
+            if ((uint64_t)L.a + L.b > sc->n_children) return fail(WRT_E_INVALID, "light collection child range out of bounds");
+            for (uint32_t k = 0; k < L.b; ++k)
+                if (!add(sc->children[L.a + k])) return false;
+        } else {
+            if (!add(sc->lights)) return false;
+        }
+        out.has_lights = true;
+        return true;
+    }
+
+    int run() {
+        if (!sc) { fail(WRT_E_INVALID, "scene is NULL"); return code; }
+        if (sc->abi_version != WRT_ABI_VERSION) { fail(WRT_E_INVALID, "wrt_scene.abi_version mismatch"); return code; }
+        if (sc->n_entities == 0 || sc->root >= sc->n_entities) { fail(WRT_E_INVALID, "scene root out of range"); return code; }
+        if ((sc->n_entities && !sc->entities) || (sc->n_children && !sc->children) || (sc->n_spheres && !sc->spheres) ||
+            (sc->n_quads && !sc->quads) || (sc->n_materials && !sc->materials) || (sc->n_textures && !sc->textures) ||
+            (sc->n_images && !sc->images)) {
+            fail(WRT_E_INVALID, "scene array pointer is NULL with a non-zero count");
+            return code;
+        }
+        tight.resize(sc->n_entities);
+        tight_state.assign(sc->n_entities, 0);
+        prim_id.assign(sc->n_entities, WRT_NONE);
+        on_stack.assign(sc->n_entities, 0);
+        if (!compile_materials() || !compile_geometry() || !compile_lights()) return code;
+        if (!emit(sc->root, WRT_NONE, 0)) return code;
+        out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
+        if (out.boxes_ref.empty()) {  // keep the device pointers non-null
+            BoxRef r = {0, 0, 0, 0};
+            out.boxes_ref.push_back(r);
+            Box3 e; e.reset();
+            out.boxes_tight.push_back(padded(e));
+        }
+        return code;
+    }
+};
+
+}  // namespace
+
+int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err) {
+    out = CompiledScene();
+    Compiler c(scene, out, err);
+    return c.run();
+}
+
+}  // namespace wrt

@@ -1,0 +1,32 @@
+// wrt_program.h — host-side "flattener": compiles the entity tree handed over the C ABI (wrt_scene) into the
+// stack-less traversal program and the 16-byte aligned record arrays the kernels read.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "wrt_device.cuh"
+
+namespace wrt {
+
+struct CompiledScene {
+    std::vector<uint4> ops;
+    std::vector<BoxRef> boxes_ref;
+    std::vector<BoxTight> boxes_tight;
+    std::vector<SphereGeom> spheres;
+    std::vector<SphereAux> sphere_aux;  // empty unless a sphere moves
+    std::vector<QuadGeom> quads;
+    std::vector<Xform> xforms;
+    std::vector<Material> materials;
+    std::vector<Texture> textures;
+    std::vector<Light> lights;
+    uint32_t n_prims = 0;
+    uint32_t max_xform_depth = 0;
+    bool has_lights = false;
+    bool has_moving = false;
+};
+
+// Returns WRT_OK or a WRT_E_* code with `err` set.
+int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err);
+
+}  // namespace wrt
