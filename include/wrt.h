@@ -192,6 +192,11 @@ typedef struct wrt_params {
 
 #define WRT_FLAG_NO_CLEAR 1u       /* add onto the existing framebuffer contents instead of clear_color */
 #define WRT_FLAG_DISABLE_DOF 2u    /* treat the camera as a pinhole (gate-1 dumps) */
+#define WRT_FLAG_FORCE_LANE 4u     /* closest-hit scan per lane even for small programs (default: chosen by program size) */
+#define WRT_FLAG_FORCE_PACKET 8u   /* warp-uniform packet scan even for large programs */
+/* the same two switches for wrt_trace_rays, OR-ed into its cull_mode argument */
+#define WRT_TRAV_FORCE_LANE 0x100u
+#define WRT_TRAV_FORCE_PACKET 0x200u
 
 typedef struct wrt_stats {
     uint64_t paths;          /* camera samples started */

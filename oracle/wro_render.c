@@ -89,6 +89,7 @@ static int material_scatter(const wro_material* m, const ray* ray_in, const wro_
         case WRO_MAT_METAL: {
             double blur = wro_clamp(m->param, 0.0, 1.0);
             v3 refl = v3_reflect(ray_in->direction, rec->normal); /* unnormalised incoming direction (A.9-8) */
+            wro_rng_slot(rng, 2);
             v3 dir = v3_add(refl, v3_scale(wro_sample_unit_sphere(rng), blur));
             sr->attenuation = m->albedo;
             sr->pdf_kind = PDF_NONE;
@@ -104,6 +105,7 @@ static int material_scatter(const wro_material* m, const ray* ray_in, const wro_
             double cos_theta = fmin(v3_dot(v3_neg(in_unit), rec->normal), 1.0);
             double sin_theta = sqrt(1 - cos_theta * cos_theta);
             v3 dir;
+            wro_rng_slot(rng, 0);
             /* `or` short-circuits: the uniform is drawn only when total internal reflection does not apply */
             if (index * sin_theta > 1.0 || reflectance(m->param, cos_theta) > wro_rng_float(rng))
                 dir = v3_reflect(in_unit, rec->normal);
@@ -154,10 +156,12 @@ typedef struct trace_ctx {
     v3 background;
     wro_rng* rng;
     uint64_t rays;
+    uint32_t max_depth;
 } trace_ctx;
 
 static v3 ray_color(trace_ctx* tc, const ray* r, uint32_t depth) {
     if (depth == 0) return v3_splat(0);
+    wro_rng_set_base(tc->rng, 4u + 4u * (tc->max_depth - depth)); /* counter mode: this bounce's draw slots */
     const double ray_correction_factor = 1e-4;
     wro_hit rec;
     memset(&rec, 0, sizeof rec);
@@ -186,15 +190,22 @@ static v3 ray_color(trace_ctx* tc, const ray* r, uint32_t depth) {
     const wro_entity* lights = tc->scene->lights;
     if (lights) {
         /* MixturePdf(EntityPdf(lights, point), material pdf): pdf.zig:99-118, render.zig:254-263 */
+        wro_rng_slot(tc->rng, 0);
         double p = wro_rng_float(tc->rng);
-        if (p < 0.5) scattered.direction = wro_entity_sample_direction(lights, tc->rng, rec.point);
-        else scattered.direction = surface_pdf_generate(sr.pdf_kind, &sr.pdf_basis, tc->rng);
+        if (p < 0.5) {
+            wro_rng_slot(tc->rng, 1);
+            scattered.direction = wro_entity_sample_direction(lights, tc->rng, rec.point);
+        } else {
+            wro_rng_slot(tc->rng, 2);
+            scattered.direction = surface_pdf_generate(sr.pdf_kind, &sr.pdf_basis, tc->rng);
+        }
         double p1 = wro_entity_pdf_value(tc->scene, lights, rec.point, scattered.direction);
         double p2 = surface_pdf_value(sr.pdf_kind, &sr.pdf_basis, scattered.direction);
         pdf_value = 0.5 * p1 + 0.5 * p2;
     } else {
         /* render.zig:264-269: a cosine pdf about the normal whatever the material asked for */
         onb basis = onb_init(rec.normal);
+        wro_rng_slot(tc->rng, 2);
         scattered.direction = surface_pdf_generate(PDF_COSINE, &basis, tc->rng);
         pdf_value = surface_pdf_value(PDF_COSINE, &basis, scattered.direction);
     }
@@ -223,6 +234,7 @@ static ray sample_ray(const wrt_camera* cam, int dof, wro_rng* rng, wro_sobol_sa
     ray r;
     r.origin = origin;
     r.direction = v3_sub(sample, origin);
+    if (rng) wro_rng_slot(rng, 2);
     r.time = rng ? wro_rng_float(rng) : 0.0;
     return r;
 }
@@ -278,7 +290,7 @@ static void* render_worker(void* argp) {
             for (uint32_t s = c->s_begin; s < c->s_end; ++s) {
                 if (c->rng_mode == WRO_RNG_COUNTER) wro_rng_start_counter(&rng, p->seed, row * p->width + col, s);
                 ray r = sample_ray(c->cam, dof, &rng, &sampler, col, row, s);
-                trace_ctx tc = {c->scene, arr3(p->background_color), &rng, 0};
+                trace_ctx tc = {c->scene, arr3(p->background_color), &rng, 0, p->max_ray_bounce_depth};
                 v3 cs = ray_color(&tc, &r, p->max_ray_bounce_depth);
                 color = v3_add(color, v3_scale(cs, scale));
                 rays += tc.rays;

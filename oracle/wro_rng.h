@@ -32,7 +32,7 @@ typedef struct wro_rng {
     int mode;
     uint64_t s[4]; /* Xoshiro256++ state */
     uint64_t seed; /* counter mode key */
-    uint32_t pixel, sample, draw;
+    uint32_t pixel, sample, draw, base;
 } wro_rng;
 
 /* ---- Xoshiro256++ / SplitMix64 (Zig std.Random.Xoshiro256 / SplitMix64) ------------------------- */
@@ -93,6 +93,17 @@ static inline void wro_rng_start_counter(wro_rng* r, uint64_t seed, uint32_t pix
     r->pixel = pixel;
     r->sample = sample;
     r->draw = 0;
+    r->base = 0;
+}
+
+/* Counter mode draw layout (shared with the device): draws 0,1 = lens sample, 2 = ray time; bounce b
+ * owns draws 4+4b .. 4+4b+3 = {mixture choice | Fresnel uniform, light pick, u1, u2}.  Fixed slots keep one Philox
+ * block per draw pair on the device.  No-ops for the reference-like generator. */
+static inline void wro_rng_set_base(wro_rng* r, uint32_t base) {
+    if (r->mode == WRO_RNG_COUNTER) { r->base = base; r->draw = base; }
+}
+static inline void wro_rng_slot(wro_rng* r, uint32_t slot) {
+    if (r->mode == WRO_RNG_COUNTER) r->draw = r->base + slot;
 }
 
 static inline uint64_t wro_rng_u64(wro_rng* r) {

@@ -13,6 +13,10 @@ WRT_CULL_TIGHT = 0
 WRT_CULL_REFERENCE = 1
 WRT_FLAG_NO_CLEAR = 1
 WRT_FLAG_DISABLE_DOF = 2
+WRT_FLAG_FORCE_LANE = 4
+WRT_FLAG_FORCE_PACKET = 8
+WRT_TRAV_FORCE_LANE = 0x100
+WRT_TRAV_FORCE_PACKET = 0x200
 
 ENT_SPHERE, ENT_QUAD, ENT_COLLECTION, ENT_BVH_NODE, ENT_TRANSLATE, ENT_ROTATE_Y = range(6)
 MAT_LAMBERTIAN, MAT_ISOTROPIC, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_EMISSIVE = range(5)

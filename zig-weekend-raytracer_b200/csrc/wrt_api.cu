@@ -92,6 +92,7 @@ struct wrt_ctx {
     DevBuf<wrt::SphereAux> d_sphere_aux;
     DevBuf<wrt::QuadGeom> d_quads;
     DevBuf<wrt::Xform> d_xforms;
+    DevBuf<uint32_t> d_xform_chains;
     DevBuf<wrt::Material> d_materials;
     DevBuf<wrt::Texture> d_textures;
     DevBuf<wrt::ImageDesc> d_images;
@@ -189,7 +190,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->free_images();
     ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_spheres.release();
-    ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_materials.release();
+    ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
     for (auto& ev : ctx->ev)
@@ -273,6 +274,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
     CU(ctx->d_quads.upload(cs.quads, ctx->stream));
     CU(ctx->d_xforms.upload(cs.xforms, ctx->stream));
+    CU(ctx->d_xform_chains.upload(cs.xform_chains, ctx->stream));
     CU(ctx->d_materials.upload(cs.materials, ctx->stream));
     CU(ctx->d_textures.upload(cs.textures, ctx->stream));
     CU(ctx->d_lights.upload(cs.lights, ctx->stream));
@@ -280,7 +282,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     wrt::DeviceScene& ds = ctx->ds;
     ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p;
     ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
-    ds.xforms = ctx->d_xforms.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
+    ds.xforms = ctx->d_xforms.p; ds.xform_chains = ctx->d_xform_chains.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
     ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p;
     ds.n_ops = (uint32_t)cs.ops.size();
     ds.n_lights = (uint32_t)cs.lights.size();
@@ -313,6 +315,13 @@ static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->sobol_w = width; ctx->sobol_h = height;
     return WRT_OK;
+}
+
+// Small programs are scanned with the warp-uniform packet traversal, large ones per lane.
+static bool use_packet(const wrt_ctx* ctx, uint32_t flags) {
+    if (flags & WRT_FLAG_FORCE_LANE) return false;
+    if (flags & WRT_FLAG_FORCE_PACKET) return true;
+    return ctx->cs.ops.size() <= WRT_PACKET_MAX_OPS;
 }
 
 static uint32_t shard_rows(const wrt_params& p) {
@@ -372,7 +381,8 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     // Job decomposition: (row x 32-column block) as in the reference (render.zig:55-73), times a sample split
     // chosen so that the persistent grid has >= 16 jobs per resident warp to balance uneven path lengths.
     int blocks_per_sm = 0;
-    CU(wrt::render_occupancy(p.cull_mode, &blocks_per_sm));
+    const bool packet = use_packet(ctx, p.flags);
+    CU(wrt::render_occupancy(p.cull_mode, packet, &blocks_per_sm));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
     const uint64_t resident_warps = (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
@@ -406,7 +416,7 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     uint32_t launches = 0;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (rc.total_jobs > 0) {
-        CU(wrt::launch_render(ctx->ds, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        CU(wrt::launch_render(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -500,7 +510,12 @@ extern "C" int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double*
     int rc_ = bind_device(ctx);
     if (rc_) return rc_;
     if (!ctx->have_scene) return ctx->fail(WRT_E_STATE, "wrt_trace_rays: no scene uploaded");
+    uint32_t trav_flags = 0;
+    if (cull_mode & WRT_TRAV_FORCE_LANE) trav_flags |= WRT_FLAG_FORCE_LANE;
+    if (cull_mode & WRT_TRAV_FORCE_PACKET) trav_flags |= WRT_FLAG_FORCE_PACKET;
+    cull_mode &= 0xFFu;
     if (cull_mode > WRT_CULL_REFERENCE) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    const bool packet = use_packet(ctx, trav_flags);
     if (n == 0) return WRT_OK;
     if (!origins || !directions) return ctx->fail(WRT_E_INVALID, "origins/directions is NULL");
     DevBuf<double> d_o, d_d, d_t, d_p, d_n, d_uv;
@@ -519,7 +534,7 @@ extern "C" int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double*
         TRY(cudaMemcpyAsync(d_o.p, origins, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         TRY(cudaMemcpyAsync(d_d.p, directions, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         uint32_t grid = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * 32);
-        TRY(wrt::launch_trace_rays(ctx->ds, cull_mode, d_o.p, d_d.p, n, tmin, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr,
+        TRY(wrt::launch_trace_rays(ctx->ds, cull_mode, packet, d_o.p, d_d.p, n, tmin, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr,
                                    point ? d_p.p : nullptr, normal ? d_n.p : nullptr, uv ? d_uv.p : nullptr,
                                    front_face ? d_ff.p : nullptr, grid, ctx->stream));
         if (prim_ids) TRY(cudaMemcpyAsync(prim_ids, d_ids.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

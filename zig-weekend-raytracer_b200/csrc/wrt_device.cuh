@@ -82,6 +82,7 @@ struct DeviceScene {
     const SphereAux* sphere_aux;
     const QuadGeom* quads;
     const Xform* xforms;
+    const uint32_t* xform_chains;  // WRT_MAX_XFORM_DEPTH ids per xform, root -> leaf, WRT_NONE padded
     const Material* materials;
     const Texture* textures;
     const ImageDesc* images;
@@ -146,12 +147,15 @@ __device__ __forceinline__ d3 onb_transform(const Onb& b, d3 p) {  // math.zig:8
 // Counter-based RNG: Philox4x32-10 keyed by the render seed, counted by (pixel, sample, draw).  The oracle
 // carries the same definition (oracle/wro_rng.h) so CPU and device paths consume identical numbers.
 // ---------------------------------------------------------------------------------------------------------
+// Draw layout: draws 0,1 = lens sample, 2 = ray time; bounce b owns draws 4+4b .. 4+4b+3 =
+// {mixture choice | Fresnel uniform, light pick, u1, u2}.  One Philox block yields the two draws of an even/odd pair.
 struct Rng {
-    uint32_t k0, k1, pixel, sample, draw;
+    uint32_t k0, k1, pixel, sample;
 };
 
-__device__ __forceinline__ uint64_t philox_bits(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t draw) {
-    uint32_t c0 = pixel, c1 = sample, c2 = draw >> 1, c3 = 0u;
+__device__ __forceinline__ void philox_block(const Rng& r, uint32_t block, uint64_t& lo, uint64_t& hi) {
+    uint32_t c0 = r.pixel, c1 = r.sample, c2 = block, c3 = 0u;
+    uint32_t k0 = r.k0, k1 = r.k1;
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -162,14 +166,19 @@ __device__ __forceinline__ uint64_t philox_bits(uint32_t k0, uint32_t k1, uint32
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    return (draw & 1u) ? ((uint64_t)c2 | ((uint64_t)c3 << 32)) : ((uint64_t)c0 | ((uint64_t)c1 << 32));
+    lo = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    hi = (uint64_t)c2 | ((uint64_t)c3 << 32);
 }
-__device__ __forceinline__ double rng_float(Rng& r) {  // Random.float(f64) stand-in: 53 bits in [0,1)
-    uint64_t bits = philox_bits(r.k0, r.k1, r.pixel, r.sample, r.draw++);
-    return (double)(bits >> 11) * 0x1p-53;
+__device__ __forceinline__ double bits_to_unit(uint64_t bits) { return (double)(bits >> 11) * 0x1p-53; }  // 53 bits in [0,1)
+// draws (2*block, 2*block + 1) as uniforms
+__device__ __forceinline__ void rng_pair(const Rng& r, uint32_t block, double& a, double& b) {
+    uint64_t lo, hi;
+    philox_block(r, block, lo, hi);
+    a = bits_to_unit(lo);
+    b = bits_to_unit(hi);
 }
-__device__ __forceinline__ uint32_t rng_pick(Rng& r, uint32_t n) {  // intRangeAtMost(0, n-1) stand-in
-    uint32_t i = (uint32_t)(rng_float(r) * (double)n);
+__device__ __forceinline__ uint32_t pick_index(double u, uint32_t n) {  // intRangeAtMost(0, n-1) stand-in
+    uint32_t i = (uint32_t)(u * (double)n);
     return i < n ? i : n - 1;
 }
 
@@ -252,13 +261,15 @@ __device__ __forceinline__ void apply_xform(const Xform& X, d3& o, d3& d) {
         d = mk(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
     }
 }
-__device__ inline void ray_in_xform(const DeviceScene& S, uint32_t xf, d3 wo, d3 wd, d3& o, d3& d) {
+__device__ __forceinline__ void ray_in_xform(const DeviceScene& S, uint32_t xf, d3 wo, d3 wd, d3& o, d3& d) {
     o = wo; d = wd;
     if (xf == WRT_NONE) return;
-    uint32_t chain[WRT_MAX_XFORM_DEPTH];
-    int n = 0;
-    for (uint32_t k = xf; k != WRT_NONE && n < WRT_MAX_XFORM_DEPTH; k = S.xforms[k].parent) chain[n++] = k;
-    for (int i = n - 1; i >= 0; --i) apply_xform(S.xforms[chain[i]], o, d);
+    const uint32_t* chain = S.xform_chains + (size_t)xf * WRT_MAX_XFORM_DEPTH;
+    for (int k = 0; k < WRT_MAX_XFORM_DEPTH; ++k) {
+        const uint32_t id = __ldg(chain + k);
+        if (id == WRT_NONE) break;
+        apply_xform(S.xforms[id], o, d);
+    }
 }
 
 template <int CULL>
@@ -375,6 +386,99 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
                     double beta = dot(bw, cross(bu, planar));
                     if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
                         best.t = t; best.pc = pc; best.xform = xf;
+                    }
+                }
+            }
+            ++pc;
+        } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
+            apply_xform(S.xforms[op.y], o, d);
+            xf = op.y;
+            cull.set_ray(o, d);
+            ++pc;
+        } else if (op.x == OP_POP) {
+            xf = op.y;
+            ray_in_xform(S, xf, wo, wd, o, d);
+            cull.set_ray(o, d);
+            ++pc;
+        } else {  // OP_END
+            break;
+        }
+    }
+    return best;
+}
+
+// Packet form of the same scan for small programs (a few dozen ops: Cornell box, emissive, ...): the program counter
+// is WARP-UNIFORM, every lane looks at the same op, and a node's subtree is skipped only when no lane of the warp
+// needs it.  There is no op-kind divergence and every scene load is a broadcast.  Each lane still sees exactly the
+// sequential scan of closest_hit(): a lane whose own box test failed is parked (`resume`) until the op after that
+// subtree, which matters for WRT_CULL_REFERENCE where the reference's boxes are not always conservative.
+// Must be called by all 32 lanes; `active` = the lane carries a ray.
+template <int CULL>
+__device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool active, d3 wo, d3 wd, double time, double tmin, double tmax) {
+    ClosestHit best;
+    best.t = tmax; best.pc = WRT_NONE; best.xform = WRT_NONE;
+    d3 o = wo, d = wd;
+    uint32_t xf = WRT_NONE;
+    Culler<CULL> cull;
+    cull.set_ray(o, d);
+    uint32_t pc = 0;      // uniform
+    uint32_t resume = 0;  // per lane: first op this lane takes part in again
+    for (;;) {
+        const uint4 op = __ldg(S.ops + pc);
+        const bool live = active && pc >= resume;
+        if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) {
+            bool pass = live;
+            if (live && !(CULL == WRT_CULL_REFERENCE && op.x == OP_NODE_TIGHT_ONLY)) {
+                pass = cull.pass(S, op.y, tmin, best.t);
+                if (!pass) resume = op.z;
+            }
+            pc = __any_sync(0xffffffffu, pass) ? pc + 1 : op.z;
+        } else if (op.x == OP_SPHERE) {
+            if (live) {
+                const double2* g = reinterpret_cast<const double2*>(S.spheres + op.y);
+                double2 g0 = __ldg(g), g1 = __ldg(g + 1);
+                d3 center = mk(g0.x, g0.y, g1.x);
+                const double radius = g1.y;
+                if (S.has_moving) {
+                    const SphereAux ax = S.sphere_aux[op.y];
+                    if (ax.is_moving) center = center + mk(ax.mx, ax.my, ax.mz) * time;
+                }
+                d3 oc = center - o;
+                double a = dot(d, d);
+                double h = dot(d, oc);
+                double c = dot(oc, oc) - radius * radius;
+                double disc = h * h - a * c;
+                if (!(disc < 0.0)) {
+                    double sq = sqrt(disc);
+                    double root = (h - sq) / a;
+                    bool ok = (tmin < root) && (root < best.t);
+                    if (!ok) {
+                        root = (h + sq) / a;
+                        ok = (tmin < root) && (root < best.t);
+                    }
+                    if (ok) { best.t = root; best.pc = pc; best.xform = xf; }
+                }
+            }
+            ++pc;
+        } else if (op.x == OP_QUAD) {
+            if (live) {
+                const double2* g = reinterpret_cast<const double2*>(S.quads + op.y);
+                double2 n0 = __ldg(g), n1 = __ldg(g + 1);
+                d3 n = mk(n0.x, n0.y, n1.x);
+                double denom = dot(n, d);
+                if (!(fabs(denom) < 1e-8)) {
+                    double t = (n1.y - dot(n, o)) / denom;
+                    if ((tmin <= t) && (t <= best.t)) {
+                        double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
+                        double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                        d3 p = o + d * t;
+                        d3 planar = p - mk(s0.x, s0.y, s1.x);
+                        d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
+                        double alpha = dot(bw, cross(planar, bv));
+                        double beta = dot(bw, cross(bu, planar));
+                        if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
+                            best.t = t; best.pc = pc; best.xform = xf;
+                        }
                     }
                 }
             }
@@ -551,54 +655,6 @@ __device__ inline double lights_pdf_value(const DeviceScene& S, d3 origin, d3 di
     double sum = 0.0;
     for (uint32_t i = 0; i < S.n_lights; ++i) sum += weight * light_pdf_value_one(S, S.lights[i], origin, direction);
     return sum;
-}
-
-__device__ inline d3 lights_sample_direction(const DeviceScene& S, Rng& rng, d3 origin) {  // entity.zig:381-386
-    const uint32_t idx = rng_pick(rng, S.n_lights);
-    const Light L = S.lights[idx];
-    if (L.kind == WRT_ENT_QUAD) {  // entity.zig:520-525
-        const QuadGeom q = S.quads[L.index];
-        double r1 = rng_float(rng);
-        d3 u = mk(q.ux, q.uy, q.uz) * r1;
-        double r2 = rng_float(rng);
-        d3 v = mk(q.vx, q.vy, q.vz) * r2;
-        d3 p = (mk(q.sx, q.sy, q.sz) + u) + v;
-        return p - origin;
-    }
-    if (L.kind == WRT_ENT_SPHERE) {  // entity.zig:646-651 + randomToSphere :668-679
-        const SphereGeom g = S.spheres[L.index];
-        d3 direction = mk(g.cx, g.cy, g.cz) - origin;
-        double dist_sq = dot(direction, direction);
-        Onb basis = onb_init(direction);
-        double r1 = rng_float(rng);
-        double r2 = rng_float(rng);
-        double z = 1.0 + r2 * (sqrt(1.0 - g.radius * g.radius / dist_sq) - 1.0);
-        double phi = 2.0 * WRT_PI * r1;
-        double sz2 = sqrt(1.0 - z * z);
-        double sn, cs;
-        sincos(phi, &sn, &cs);
-        return onb_transform(basis, mk(cs * sz2, sn * sz2, z));
-    }
-    return mk(1, 0, 0);  // entity.zig:58-65
-}
-
-__device__ __forceinline__ d3 sample_cosine_direction_z(Rng& rng) {  // rng.zig:104-114
-    double r1 = rng_float(rng);
-    double r2 = rng_float(rng);
-    double phi = 2.0 * WRT_PI * r1;
-    double sn, cs;
-    sincos(phi, &sn, &cs);
-    double sr2 = sqrt(r2);
-    return mk(cs * sr2, sn * sr2, sqrt(1.0 - r2));
-}
-__device__ __forceinline__ d3 sample_unit_sphere(Rng& rng) {  // rng.zig:87-95 (direct form)
-    double u1 = rng_float(rng), u2 = rng_float(rng);
-    double z = 1.0 - 2.0 * u1;
-    double s = sqrt(fmax(0.0, 1.0 - z * z));
-    double phi = 2.0 * WRT_PI * u2;
-    double sn, cs;
-    sincos(phi, &sn, &cs);
-    return mk(cs * s, sn * s, z);
 }
 
 // writer.zig:68-94 encodeColor: NaN -> 0, sqrt, clamp [0, 0.999], * 256, truncate

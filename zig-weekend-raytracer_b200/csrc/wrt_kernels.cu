@@ -1,14 +1,17 @@
 // wrt_kernels.cu — sm_100a kernels of the render back end.
 //
-//   render_kernel<CULL>      persistent warps pull (row, 32-column block, sample chunk) jobs — the reference's job
+//   render_kernel<CULL,TRAV> persistent warps pull (row, 32-column block, sample chunk) jobs — the reference's job
 //                            shape (render.zig:55-73) times a sample split — and run the iterative form of rayColor
 //                            (render.zig:188-289).  Each lane owns one pixel of the block and
 //                            regenerates a new camera sample as soon as its path ends, so lanes never idle while
 //                            the pixel still has samples; per-(pixel, chunk) sums go to a private slot.
+//                            TRAV selects the closest-hit scan: warp-uniform packet (small programs) or per-lane.
 //   resolve_kernel           fused final pass: clear colour + ordered sum of the chunk slots -> caller's f64
 //                            framebuffer layout, and encodeColor (writer.zig:68-94) into RGB8.
 //   primary_hits_kernel / trace_rays_kernel / sobol_*_kernel   gates and diagnostics (include/wrt.h).
 #include <math_constants.h>
+
+#include <type_traits>
 
 #include "wrt_device.cuh"
 #include "wrt_kernels.h"
@@ -27,8 +30,10 @@ cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stre
 
 __device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
-// sampleRay, render.zig:144-174 (+ sampleDefocusDisk :182-185, rng.sampleUnitDiskXY rng.zig:76-78)
-__device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, bool dof, Rng* rng) {
+// sampleRay, render.zig:144-174 (+ sampleDefocusDisk :182-185, rng.sampleUnitDiskXY rng.zig:76-78).
+// rng == nullptr: gate-1 dump (pinhole, time 0).  Draws: block 0 = (lens radius, lens angle), block 1.lo = time.
+__device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, bool dof, bool need_time,
+                                          const Rng* rng) {
     uint64_t idx = sobol_interval_to_index(c_sobol, s, col, row);
     double ox, oy;
     sobol_pixel_2d(c_sobol, idx, col, row, ox, oy);
@@ -36,10 +41,11 @@ __device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t co
                 ld3(rc.cam.pixel_delta_v) * ((double)row + oy);
     d3 origin = ld3(rc.cam.position);
     if (dof) {
-        double rr = 1.0 * rng_float(*rng);  // radius * float, evaluated before the circle sample
-        double phi = 2.0 * WRT_PI * rng_float(*rng);
+        double ur, ua;
+        rng_pair(*rng, 0, ur, ua);
+        double rr = 1.0 * ur;  // radius * float, evaluated before the circle sample (linear radius, A.9-9)
         double sn, cs;
-        sincos(phi, &sn, &cs);
+        sincos(2.0 * WRT_PI * ua, &sn, &cs);
         d3 p = mk(cs, sn, 0.0) * rr;
         origin = (ld3(rc.cam.position) + ld3(rc.cam.defocus_disk_u) * p.x) + ld3(rc.cam.defocus_disk_v) * p.y;
     }
@@ -47,9 +53,10 @@ __device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t co
     r.o = origin;
     r.d = sample - origin;
     r.time = 0.0;
-    if (rng) {
-        // time = rand.float (render.zig:167): the draw is always consumed; the value only matters for moving spheres
-        r.time = rng_float(*rng);
+    if (need_time) {  // time = rand.float (render.zig:167); only moving spheres read it
+        double ut, unused;
+        rng_pair(*rng, 1, ut, unused);
+        r.time = ut;
     }
     return r;
 }
@@ -63,77 +70,145 @@ __device__ __forceinline__ double reflectance(double ir, double cosine) {
     return r0 + (1 - r0) * (x2 * x2 * x);
 }
 
-// One bounce of rayColor in throughput form.  Returns false when the path ends.
+// texture.value with the common case (solid colour) inline and everything else out of line
+__device__ __noinline__ d3 texture_value_general(const DeviceScene& S, uint32_t tex, double u, double v, d3 point, d3 outward, bool is_sphere) {
+    if (is_sphere && texture_needs_uv(S, tex)) sphere_uv(outward, u, v);  // lazily: acos + atan2 (entity.zig:659-666)
+    return texture_value(S, tex, u, v, point);
+}
+__device__ __forceinline__ d3 texture_color(const DeviceScene& S, uint32_t tex, const HitRecord& rec) {
+    const Texture T = S.textures[tex];
+    if (T.kind == WRT_TEX_SOLID) return mk(T.r, T.g, T.b);
+    return texture_value_general(S, tex, rec.u, rec.v, rec.point, rec.sphere_outward, rec.is_sphere != 0);
+}
+
+enum SampleMode { SM_FIXED = 0, SM_LIGHT_QUAD, SM_COSINE, SM_SPHERE_UNIFORM, SM_LIGHT_SPHERE };
+
+// One bounce of rayColor in throughput form, given the closest hit.  Returns false when the path ends.
 //   L    += beta * emitted                     (render.zig:234,288)
 //   beta *= attenuation [* scatteringPdf/pdf]  (render.zig:245, 282-285)
-template <int CULL>
-__device__ __forceinline__ bool path_step(const DeviceScene& S, const RenderConstants& rc, Ray& ray, d3& beta, d3& L, Rng& rng,
-                                          unsigned long long& n_rays) {
-    ++n_rays;
-    const ClosestHit ch = closest_hit<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+// All direction sampling (cosine lobe, uniform sphere, cone towards a sphere light) funnels through ONE sincos +
+// ONE orthonormal-basis site, selected per lane, so that the lanes of a warp stay together whatever they sample.
+__device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstants& rc, const ClosestHit& ch, Ray& ray, d3& beta, d3& L,
+                                      const Rng& rng, uint32_t bounce) {
     if (ch.pc == WRT_NONE) {  // render.zig:215-217
         L = L + beta * ld3(rc.background);
         return false;
     }
-    const uint32_t mat_id = __ldg(&S.ops[ch.pc].z);
-    const Material M = S.materials[mat_id];
-    const bool textured = (M.kind == WRT_MAT_LAMBERTIAN || M.kind == WRT_MAT_ISOTROPIC || M.kind == WRT_MAT_DIFFUSE_EMISSIVE);
-    const bool want_uv = textured && texture_needs_uv(S, M.texture);
     HitRecord rec;
-    resolve_hit(S, ch, ray.o, ray.d, ray.time, want_uv, rec);
+    resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec);
+    const Material M = S.materials[rec.material];
+    const uint32_t block_a = 2u + 2u * bounce, block_b = block_a + 1u;
 
     if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) {  // material.zig:88-96; no scatter => return emission (render.zig:238-240)
-        // back faces emit 0; the product is still formed so that a NaN/inf throughput poisons the sample as it does
-        // in the reference's recursion (0 * NaN), which the writer later zeroes (writer.zig:72-94)
-        d3 e = rec.front_face ? texture_value(S, M.texture, rec.u, rec.v, rec.point) : mk(0, 0, 0);
+        // back faces emit 0; the product is still formed so that a NaN/inf throughput poisons the sample as it does in the
+        // reference's recursion (0 * NaN), which the writer later zeroes (writer.zig:72-94)
+        d3 e = rec.front_face ? texture_color(S, M.texture, rec) : mk(0, 0, 0);
         L = L + beta * e;
         return false;
-    }
-    if (M.kind == WRT_MAT_METAL) {  // material.zig:163-178
-        double blur = clamp01(M.param);
-        d3 refl = reflect(ray.d, rec.normal);
-        d3 dir = refl + sample_unit_sphere(rng) * blur;
-        if (!(dot(dir, rec.normal) > 0.0)) {  // scatter false => emission (0)
-            L = L + beta * 0.0;
-            return false;
-        }
-        beta = beta * mk(M.ar, M.ag, M.ab);
-        ray.o = rec.point;
-        ray.d = dir;
-        return true;
     }
     if (M.kind == WRT_MAT_DIELECTRIC) {  // material.zig:190-218
         double index = rec.front_face ? 1.0 / M.param : M.param;
         d3 in_unit = normalize(ray.d);
         double cos_theta = fmin(dot(-in_unit, rec.normal), 1.0);
         double sin_theta = sqrt(1 - cos_theta * cos_theta);
+        double u0, unused;
+        rng_pair(rng, block_a, u0, unused);
         d3 dir;
-        if (index * sin_theta > 1.0 || reflectance(M.param, cos_theta) > rng_float(rng)) dir = reflect(in_unit, rec.normal);
+        if (index * sin_theta > 1.0 || reflectance(M.param, cos_theta) > u0) dir = reflect(in_unit, rec.normal);
         else dir = refract(in_unit, rec.normal, index);
         ray.o = rec.point;  // attenuation (1,1,1)
         ray.d = dir;
         return true;
     }
-    // lambertian / isotropic: importance-sampled diffuse bounce (render.zig:248-288)
-    const d3 attenuation = texture_value(S, M.texture, rec.u, rec.v, rec.point);
-    const bool cosine_pdf = (M.kind == WRT_MAT_LAMBERTIAN) || !S.has_lights;  // render.zig:264-269 forces cosine without lights
-    Onb basis;
-    if (cosine_pdf) basis = onb_init(rec.normal);
-    d3 dir;
-    double pdf_value;
-    if (S.has_lights) {  // MixturePdf(EntityPdf(lights), material pdf), pdf.zig:99-118
-        double p = rng_float(rng);
-        if (p < 0.5) dir = lights_sample_direction(S, rng, rec.point);
-        else dir = cosine_pdf ? onb_transform(basis, sample_cosine_direction_z(rng)) : sample_unit_sphere(rng);
-        double p1 = lights_pdf_value(S, rec.point, dir);
-        double p2 = cosine_pdf ? fmax(0.0, dot(normalize(dir), basis.w) / WRT_PI) : 1.0 / (4.0 * WRT_PI);
-        pdf_value = 0.5 * p1 + 0.5 * p2;
-    } else {
-        dir = onb_transform(basis, sample_cosine_direction_z(rng));
-        pdf_value = fmax(0.0, dot(normalize(dir), basis.w) / WRT_PI);
+
+    // ---- metal / lambertian / isotropic: choose what to sample -------------------------------------------------
+    const bool diffuse = (M.kind != WRT_MAT_METAL);
+    int mode = SM_SPHERE_UNIFORM;  // metal fuzz (material.zig:167-168) and the isotropic SpherePdf (pdf.zig:40-42)
+    d3 attenuation = mk(M.ar, M.ag, M.ab);
+    d3 w_n = mk(0, 0, 0);      // normalised shading normal = CosinePdf.basis.w
+    d3 axis_w = mk(0, 0, 1);   // normalised axis of the sampling frame
+    bool cosine_pdf = false;
+    double cone = 0.0;         // sqrt(1 - r^2/dist^2) of the picked sphere light
+    uint32_t light_quad = 0;   // picked quad light
+    if (diffuse) {
+        attenuation = texture_color(S, M.texture, rec);
+        cosine_pdf = (M.kind == WRT_MAT_LAMBERTIAN) || !S.has_lights;  // render.zig:264-269 forces cosine without lights
+        if (cosine_pdf) { w_n = normalize(rec.normal); mode = SM_COSINE; axis_w = w_n; }
+        if (S.has_lights) {  // MixturePdf.generate, pdf.zig:113-117
+            double p, upick;
+            rng_pair(rng, block_a, p, upick);
+            if (p < 0.5) {  // EntityCollection.sampleDirectionToSurface, entity.zig:381-386
+                const Light Lt = S.lights[pick_index(upick, S.n_lights)];
+                if (Lt.kind == WRT_ENT_QUAD) {
+                    mode = SM_LIGHT_QUAD;
+                    light_quad = Lt.index;
+                } else if (Lt.kind == WRT_ENT_SPHERE) {  // entity.zig:646-651
+                    mode = SM_LIGHT_SPHERE;
+                    const SphereGeom g = S.spheres[Lt.index];
+                    d3 to_light = mk(g.cx, g.cy, g.cz) - rec.point;
+                    double dist_sq = dot(to_light, to_light);
+                    axis_w = normalize(to_light);
+                    cone = sqrt(1.0 - g.radius * g.radius / dist_sq);
+                } else {
+                    mode = SM_FIXED;  // entity.zig:58-65
+                }
+            }
+        }
     }
+
+    // ---- the one sampling site -------------------------------------------------------------------------------------
+    double u1, u2;
+    rng_pair(rng, block_b, u1, u2);
+    d3 dir;
+    if (mode >= SM_COSINE) {
+        double phi_u, s, z;
+        if (mode == SM_COSINE) {  // rng.sampleCosineDirectionZ, rng.zig:104-114
+            phi_u = u1; s = sqrt(u2); z = sqrt(1.0 - u2);
+        } else if (mode == SM_SPHERE_UNIFORM) {  // rng.sampleUnitSphere in direct form
+            z = 1.0 - 2.0 * u1; s = sqrt(fmax(0.0, 1.0 - z * z)); phi_u = u2;
+        } else {  // randomToSphere, entity.zig:668-679
+            z = 1.0 + u2 * (cone - 1.0); s = sqrt(1.0 - z * z); phi_u = u1;
+        }
+        double sn, cs;
+        sincos(2.0 * WRT_PI * phi_u, &sn, &cs);
+        d3 local = mk(cs * s, sn * s, z);
+        if (mode == SM_SPHERE_UNIFORM) {
+            dir = local;
+        } else {  // OrthoBasis.init + transform, math.zig:65-73, 89-95
+            d3 a = (fabs(axis_w.y) > 0.9) ? mk(1, 0, 0) : mk(0, 1, 0);
+            d3 bu = normalize(cross(axis_w, a));
+            d3 bv = cross(axis_w, bu);
+            dir = (bu * local.x + bv * local.y) + axis_w * local.z;
+        }
+    } else if (mode == SM_LIGHT_QUAD) {  // QuadEntity.sampleDirectionToSurface, entity.zig:520-525
+        const QuadGeom lq = S.quads[light_quad];
+        d3 pu = mk(lq.ux, lq.uy, lq.uz) * u1;
+        d3 pv = mk(lq.vx, lq.vy, lq.vz) * u2;
+        dir = ((mk(lq.sx, lq.sy, lq.sz) + pu) + pv) - rec.point;
+    } else {
+        dir = mk(1, 0, 0);
+    }
+
+    if (!diffuse) {  // MetalMaterial.scatter, material.zig:163-178 (reflects the unnormalised direction, A.9-8)
+        double blur = clamp01(M.param);
+        d3 out = reflect(ray.d, rec.normal) + dir * blur;
+        if (!(dot(out, rec.normal) > 0.0)) {  // scatter false => return emission (0), still weighted
+            L = L + beta * 0.0;
+            return false;
+        }
+        beta = beta * attenuation;
+        ray.o = rec.point;
+        ray.d = out;
+        return true;
+    }
+
+    // ---- diffuse weights: attenuation * scatteringPdf / pdf (render.zig:280-285) -----------------------------------
+    const d3 dir_unit = normalize(dir);
+    const double surface_pdf = cosine_pdf ? fmax(0.0, dot(dir_unit, w_n) / WRT_PI) : 1.0 / (4.0 * WRT_PI);  // pdf.zig:58-61, 36-38
+    double pdf_value = surface_pdf;
+    if (S.has_lights) pdf_value = 0.5 * lights_pdf_value(S, rec.point, dir) + 0.5 * surface_pdf;  // MixturePdf.value, pdf.zig:106-111
     double sp;  // material.scatteringPdf, material.zig:118-125 / 145-150
-    if (M.kind == WRT_MAT_LAMBERTIAN) sp = fmax(0.0, dot(rec.normal, normalize(dir)) / WRT_PI);
+    if (M.kind == WRT_MAT_LAMBERTIAN) sp = fmax(0.0, dot(rec.normal, dir_unit) / WRT_PI);
     else sp = 1.0 / (4.0 * WRT_PI);
     beta = (beta * (attenuation * sp)) / pdf_value;
     ray.o = rec.point;
@@ -141,22 +216,26 @@ __device__ __forceinline__ bool path_step(const DeviceScene& S, const RenderCons
     return true;
 }
 
-template <int CULL>
-__global__ void __launch_bounds__(WRT_RENDER_BLOCK) render_kernel(DeviceScene S, double* __restrict__ accum,
-                                                                  unsigned long long* __restrict__ counters) {
+enum { TRAV_LANE = 0, TRAV_PACKET = 1 };
+
+template <int CULL, int TRAV>
+__global__ void __launch_bounds__(WRT_RENDER_BLOCK, WRT_RENDER_MIN_BLOCKS) render_kernel(DeviceScene S, double* __restrict__ accum,
+                                                                                         unsigned long long* __restrict__ counters) {
     const RenderConstants& rc = c_rc;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long n_rays = 0, n_paths = 0;
     const double scale = 1.0 / (double)rc.spp;  // pixel_color_scale, render.zig:123
     const bool dof = rc.dof != 0;
-    const uint32_t k0 = (uint32_t)rc.seed, k1 = (uint32_t)(rc.seed >> 32);
+    const bool need_time = S.has_moving != 0;
+    Rng rng;
+    rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
 
     for (;;) {
         unsigned long long job = 0;
         if (lane == 0) job = atomicAdd(&counters[0], 1ull);
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= rc.total_jobs) break;
-        // job -> (chunk, local row, column block); chunks outermost so that late jobs are the short ones
+        // job -> (chunk, local row, column block); chunks outermost
         const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
         const uint32_t chunk = (uint32_t)(job / blocks_per_chunk);
         const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
@@ -172,14 +251,15 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK) render_kernel(DeviceScene S,
         bool alive = false;
         uint32_t depth_left = 0;
         Ray ray;
+        ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
         d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
-        Rng rng;
-        rng.k0 = k0; rng.k1 = k1; rng.pixel = row * rc.width + col; rng.sample = 0; rng.draw = 0;
+        rng.pixel = row * rc.width + col;
+        rng.sample = 0;
 
         for (;;) {
             if (!alive && lane_active && s < s_last) {
-                rng.sample = s; rng.draw = 0;
-                ray = sample_ray(rc, col, row, s, dof, &rng);
+                rng.sample = s;
+                ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
                 beta = mk(1, 1, 1); L = mk(0, 0, 0);
                 depth_left = rc.max_depth;
                 alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
@@ -190,12 +270,20 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK) render_kernel(DeviceScene S,
                 if (!__any_sync(0xffffffffu, lane_active && s < s_last)) break;
                 continue;
             }
+            ClosestHit ch;
+            if (TRAV == TRAV_PACKET) {
+                ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+            } else {
+                ch.pc = WRT_NONE;
+                if (alive) ch = closest_hit<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+            }
             if (alive) {
-                bool cont = path_step<CULL>(S, rc, ray, beta, L, rng, n_rays);
+                ++n_rays;
+                const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
                 --depth_left;
                 if (!cont || depth_left == 0) {
                     if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
-                    color = color + L * scale;  // render.zig:129-135
+                    color = color + L * scale;     // render.zig:129-135
                     alive = false;
                     ++s;
                 }
@@ -257,20 +345,32 @@ __global__ void primary_hits_kernel(DeviceScene S, uint32_t n_samples, uint32_t*
         uint32_t s = (uint32_t)(i % n_samples);
         uint64_t pix = i / n_samples;
         uint32_t col = (uint32_t)(pix % rc.width), row = (uint32_t)(pix / rc.width);
-        Ray r = sample_ray(rc, col, row, s, false, nullptr);
+        Ray r = sample_ray(rc, col, row, s, false, false, nullptr);
         ClosestHit ch = closest_hit<CULL>(S, r.o, r.d, 0.0, 1e-4, CUDART_INF);
         if (ids) ids[i] = (ch.pc == WRT_NONE) ? WRT_NONE : __ldg(&S.ops[ch.pc].w);
         if (ts) ts[i] = (ch.pc == WRT_NONE) ? CUDART_INF : ch.t;
     }
 }
 
-template <int CULL>
+template <int CULL, int TRAV>
 __global__ void trace_rays_kernel(DeviceScene S, const double* __restrict__ origins, const double* __restrict__ dirs, uint64_t n,
                                   double tmin, uint32_t* ids, double* ts, double* point, double* normal, double* uv,
                                   uint32_t* front_face) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        d3 o = ld3(origins + 3 * i), d = ld3(dirs + 3 * i);
-        ClosestHit ch = closest_hit<CULL>(S, o, d, 0.0, tmin, CUDART_INF);
+    // whole warps iterate together so that the packet scan can be exercised through this entry point too
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool active = i < n;
+        d3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+        if (active) { o = ld3(origins + 3 * i); d = ld3(dirs + 3 * i); }
+        ClosestHit ch;
+        if (TRAV == TRAV_PACKET) {
+            ch = closest_hit_packet<CULL>(S, active, o, d, 0.0, tmin, CUDART_INF);
+        } else {
+            ch.pc = WRT_NONE;
+            if (active) ch = closest_hit<CULL>(S, o, d, 0.0, tmin, CUDART_INF);
+        }
+        if (!active) continue;
         const bool hit = ch.pc != WRT_NONE;
         HitRecord rec;
         if (hit) resolve_hit(S, ch, o, d, 0.0, true, rec);
@@ -323,16 +423,31 @@ cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------
-cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
-                          cudaStream_t stream) {
-    if (cull_mode == WRT_CULL_REFERENCE) render_kernel<WRT_CULL_REFERENCE><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
-    else render_kernel<WRT_CULL_TIGHT><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+template <typename F>
+static cudaError_t dispatch(uint32_t cull_mode, bool packet, F&& f) {
+    if (cull_mode == WRT_CULL_REFERENCE) {
+        if (packet) f(std::integral_constant<int, WRT_CULL_REFERENCE>(), std::integral_constant<int, TRAV_PACKET>());
+        else f(std::integral_constant<int, WRT_CULL_REFERENCE>(), std::integral_constant<int, TRAV_LANE>());
+    } else {
+        if (packet) f(std::integral_constant<int, WRT_CULL_TIGHT>(), std::integral_constant<int, TRAV_PACKET>());
+        else f(std::integral_constant<int, WRT_CULL_TIGHT>(), std::integral_constant<int, TRAV_LANE>());
+    }
     return cudaGetLastError();
 }
-cudaError_t render_occupancy(uint32_t cull_mode, int* blocks_per_sm) {
-    if (cull_mode == WRT_CULL_REFERENCE)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<WRT_CULL_REFERENCE>, WRT_RENDER_BLOCK, 0);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<WRT_CULL_TIGHT>, WRT_RENDER_BLOCK, 0);
+
+cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
+                          cudaStream_t stream) {
+    return dispatch(cull_mode, packet, [&](auto c, auto t) {
+        render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+    });
+}
+cudaError_t render_occupancy(uint32_t cull_mode, bool packet, int* blocks_per_sm) {
+    cudaError_t err = cudaSuccess;
+    dispatch(cull_mode, packet, [&](auto c, auto t) {
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<decltype(c)::value, decltype(t)::value>,
+                                                            WRT_RENDER_BLOCK, 0);
+    });
+    return err;
 }
 cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
                            uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream) {
@@ -352,14 +467,13 @@ cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32
     else primary_hits_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(S, n_samples, ids, ts);
     return cudaGetLastError();
 }
-cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, const double* origins, const double* dirs, uint64_t n, double tmin,
-                              uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face, uint32_t grid,
-                              cudaStream_t stream) {
-    if (cull_mode == WRT_CULL_REFERENCE)
-        trace_rays_kernel<WRT_CULL_REFERENCE><<<grid, 128, 0, stream>>>(S, origins, dirs, n, tmin, ids, ts, point, normal, uv, front_face);
-    else
-        trace_rays_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(S, origins, dirs, n, tmin, ids, ts, point, normal, uv, front_face);
-    return cudaGetLastError();
+cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool packet, const double* origins, const double* dirs, uint64_t n,
+                              double tmin, uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face,
+                              uint32_t grid, cudaStream_t stream) {
+    return dispatch(cull_mode, packet, [&](auto c, auto t) {
+        trace_rays_kernel<decltype(c)::value, decltype(t)::value><<<grid, 128, 0, stream>>>(S, origins, dirs, n, tmin, ids, ts, point, normal,
+                                                                                              uv, front_face);
+    });
 }
 cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
                                double* offsets, cudaStream_t stream) {

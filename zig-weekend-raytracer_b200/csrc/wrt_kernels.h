@@ -7,6 +7,11 @@
 #include "../../include/wrt.h"
 
 #define WRT_RENDER_BLOCK 128
+#ifndef WRT_RENDER_MIN_BLOCKS
+#define WRT_RENDER_MIN_BLOCKS 4  // <= 128 registers per thread: 16 warps per SM
+#endif
+// Programs up to this many ops are scanned with the warp-uniform packet traversal.
+#define WRT_PACKET_MAX_OPS 96u
 
 namespace wrt {
 
@@ -28,22 +33,21 @@ struct RenderConstants {
 cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream);
 cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream);
 
-cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream);
-cudaError_t render_occupancy(uint32_t cull_mode, int* blocks_per_sm);
+cudaError_t render_occupancy(uint32_t cull_mode, bool packet, int* blocks_per_sm);
 cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
                            uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream);
 cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* rgb8, cudaStream_t stream);
 cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
                                 cudaStream_t stream);
-cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, const double* origins, const double* dirs, uint64_t n, double tmin,
-                              uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face, uint32_t grid,
-                              cudaStream_t stream);
+cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool packet, const double* origins, const double* dirs, uint64_t n,
+                              double tmin, uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face,
+                              uint32_t grid, cudaStream_t stream);
 cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
                                double* offsets, cudaStream_t stream);
 cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
                                    uint32_t owen_fast, uint32_t seed, float* out, cudaStream_t stream);
-
 cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream);
 
 }  // namespace wrt

@@ -347,6 +347,14 @@ struct Compiler {
         if (!compile_materials() || !compile_geometry() || !compile_lights()) return code;
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
+        // transform chains in application order (outermost first), so the device needs no per-thread array
+        out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
+        for (size_t x = 0; x < out.xforms.size(); ++x) {
+            uint32_t tmp[WRT_MAX_XFORM_DEPTH];
+            int n = 0;
+            for (uint32_t k = (uint32_t)x; k != WRT_NONE && n < WRT_MAX_XFORM_DEPTH; k = out.xforms[k].parent) tmp[n++] = k;
+            for (int i = 0; i < n; ++i) out.xform_chains[x * WRT_MAX_XFORM_DEPTH + (size_t)i] = tmp[n - 1 - i];
+        }
         if (out.boxes_ref.empty()) {  // keep the device pointers non-null
             BoxRef r = {0, 0, 0, 0};
             out.boxes_ref.push_back(r);

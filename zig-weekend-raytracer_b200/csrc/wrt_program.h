@@ -17,6 +17,7 @@ struct CompiledScene {
     std::vector<SphereAux> sphere_aux;  // empty unless a sphere moves
     std::vector<QuadGeom> quads;
     std::vector<Xform> xforms;
+    std::vector<uint32_t> xform_chains;  // WRT_MAX_XFORM_DEPTH ids per xform: the chain root -> leaf, WRT_NONE padded
     std::vector<Material> materials;
     std::vector<Texture> textures;
     std::vector<Light> lights;
