@@ -106,6 +106,10 @@ struct wrt_ctx {
     DevBuf<double> d_fb;
     DevBuf<uint8_t> d_rgb8;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<wrt::PathState> d_wf_paths;      // wavefront engine: path pool, queues, counters
+    DevBuf<uint32_t> d_wf_queues;
+    DevBuf<unsigned long long> d_wf_counters;
+    unsigned long long* h_wf_counters = nullptr;  // pinned
     uint32_t last_pixels = 0;        // pixels of the last render (this shard)
     bool last_valid = false;
     uint32_t sobol_w = 0, sobol_h = 0;  // resolution the constant Sobol tables were loaded for
@@ -193,6 +197,8 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
+    ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_counters.release();
+    if (ctx->h_wf_counters) cudaFreeHost(ctx->h_wf_counters);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -387,8 +393,20 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
     const uint64_t resident_warps = (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
+    // Engine: the wavefront (queues in HBM, one small kernel per stage) wins as soon as there is enough work to fill its
+    // path pool; the persistent megakernel serves small renders and the degenerate depth-0 frame.
+    bool wavefront = (uint64_t)n_pixels64 * n_samples >= (1ull << 20) && p.max_ray_bounce_depth > 0;
+    if (p.flags & WRT_FLAG_ENGINE_MEGAKERNEL) wavefront = false;
+    if ((p.flags & WRT_FLAG_ENGINE_WAVEFRONT) && p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0) wavefront = true;
     uint32_t n_chunks = 1;
-    if (base_jobs > 0 && n_samples > 0) {
+    if (wavefront) {
+        // pool of ~4M path slots: slot = (sample chunk, pixel)
+        uint64_t want = ((4ull << 20) + n_pixels64 - 1) / n_pixels64;
+        if (want < 1) want = 1;
+        if (want > 64) want = 64;
+        if (want > n_samples) want = n_samples;
+        n_chunks = (uint32_t)want;
+    } else if (base_jobs > 0 && n_samples > 0) {
         uint64_t want = (16 * resident_warps + base_jobs - 1) / base_jobs;
         if (want < 1) want = 1;
         if (want > 64) want = 64;
@@ -415,7 +433,39 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     uint32_t launches = 0;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (rc.total_jobs > 0) {
+    unsigned long long wf_rays = 0, wf_paths = 0;
+    if (wavefront && rc.total_jobs > 0) {
+        const uint64_t n_slots64 = (uint64_t)rc.n_chunks * n_pixels64;
+        if (n_slots64 > 0xFFFFFF00ull) return ctx->fail(WRT_E_LIMIT, "wavefront pool exceeds 2^32 slots");
+        const uint32_t n_slots = (uint32_t)n_slots64;
+        CU(ctx->d_wf_paths.ensure(n_slots));
+        CU(ctx->d_wf_queues.ensure((size_t)wrt::WQ_COUNT * n_slots));
+        CU(ctx->d_wf_counters.ensure(16));
+        if (!ctx->h_wf_counters) CU(cudaMallocHost(&ctx->h_wf_counters, 16 * sizeof(unsigned long long)));
+        wrt::WavefrontArgs A;
+        A.paths = ctx->d_wf_paths.p; A.queues = ctx->d_wf_queues.p; A.counters = ctx->d_wf_counters.p;
+        A.accum = ctx->d_accum.p; A.capacity = n_slots; A.n_pixels = n_pixels;
+        CU(cudaMemsetAsync(A.counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+        const uint32_t wf_grid = (uint32_t)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        CU(wrt::wf_launch_init(A, wf_grid, ctx->stream));
+        ++launches;
+        // every slot runs chunk_size paths of at most max_depth segments, one segment per iteration
+        const uint64_t max_iters = (uint64_t)rc.chunk_size * p.max_ray_bounce_depth + 8;
+        const uint32_t check_every = 16;
+        bool done = false;
+        for (uint64_t it = 0; it < max_iters && !done; ++it) {
+            CU(wrt::wf_launch_iteration(A, ctx->ds, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
+            launches += 6;
+            if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
+                CU(cudaMemcpyAsync(ctx->h_wf_counters, A.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                done = ctx->h_wf_counters[10] >= n_slots;
+            }
+        }
+        if (!done) return ctx->fail(WRT_E_STATE, "wavefront did not drain within its iteration bound");
+        wf_rays = ctx->h_wf_counters[8];
+        wf_paths = ctx->h_wf_counters[9];
+    } else if (rc.total_jobs > 0) {
         CU(wrt::launch_render(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         ++launches;
     }
@@ -432,8 +482,8 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     float ms_total = 0, ms_kernel = 0;
     CU(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[3]));
     CU(cudaEventElapsedTime(&ms_kernel, ctx->ev[1], ctx->ev[2]));
-    ctx->stats.rays = counters[1];
-    ctx->stats.paths = counters[2];
+    ctx->stats.rays = wavefront ? wf_rays : counters[1];
+    ctx->stats.paths = wavefront ? wf_paths : counters[2];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;
     ctx->stats.kernel_launches = launches;

@@ -83,45 +83,51 @@ __device__ __forceinline__ d3 texture_color(const DeviceScene& S, uint32_t tex, 
 
 enum SampleMode { SM_FIXED = 0, SM_LIGHT_QUAD, SM_COSINE, SM_SPHERE_UNIFORM, SM_LIGHT_SPHERE };
 
-// One bounce of rayColor in throughput form, given the closest hit.  Returns false when the path ends.
+// ---- one bounce of rayColor in throughput form (render.zig:188-289), split by material class -------------
 //   L    += beta * emitted                     (render.zig:234,288)
 //   beta *= attenuation [* scatteringPdf/pdf]  (render.zig:245, 282-285)
-// All direction sampling (cosine lobe, uniform sphere, cone towards a sphere light) funnels through ONE sincos +
-// ONE orthonormal-basis site, selected per lane, so that the lanes of a warp stay together whatever they sample.
-__device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstants& rc, const ClosestHit& ch, Ray& ray, d3& beta, d3& L,
-                                      const Rng& rng, uint32_t bounce) {
-    if (ch.pc == WRT_NONE) {  // render.zig:215-217
-        L = L + beta * ld3(rc.background);
-        return false;
-    }
-    HitRecord rec;
-    resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec);
-    const Material M = S.materials[rec.material];
+// Each function returns false when the path ends.  Draw slots of bounce b: Philox blocks 2+2b (choice | Fresnel, pick)
+// and 3+2b (u1, u2).
+
+// DiffuseLightEmissiveMaterial: no scatter => return emission (material.zig:88-96, render.zig:238-240).  Back faces emit 0;
+// the product is still formed so that a NaN/inf throughput poisons the sample as it does in the reference's recursion
+// (0 * NaN), which the writer later zeroes (writer.zig:72-94).
+__device__ __forceinline__ bool shade_emissive(const DeviceScene& S, const HitRecord& rec, const Material& M, const d3& beta, d3& L) {
+    d3 e = rec.front_face ? texture_color(S, M.texture, rec) : mk(0, 0, 0);
+    L = L + beta * e;
+    return false;
+}
+
+// DielectricMaterial.scatter, material.zig:190-218 (attenuation (1,1,1))
+__device__ __forceinline__ bool shade_dielectric(const HitRecord& rec, const Material& M, Ray& ray, const Rng& rng, uint32_t bounce) {
+    double index = rec.front_face ? 1.0 / M.param : M.param;
+    d3 in_unit = normalize(ray.d);
+    double cos_theta = fmin(dot(-in_unit, rec.normal), 1.0);
+    double sin_theta = sqrt(1 - cos_theta * cos_theta);
+    double u0, unused;
+    rng_pair(rng, 2u + 2u * bounce, u0, unused);
+    d3 dir;
+    if (index * sin_theta > 1.0 || reflectance(M.param, cos_theta) > u0) dir = reflect(in_unit, rec.normal);
+    else dir = refract(in_unit, rec.normal, index);
+    ray.o = rec.point;
+    ray.d = dir;
+    return true;
+}
+
+// x / y where x == 0 is frequent (a light-sampled direction below the horizon zeroes the throughput, and the reference keeps
+// tracing that path): IEEE gives +-0 for finite non-zero y, and nvcc's division sends a zero numerator down its ~100
+// instruction slow path.  Same result bits, none of the cost.
+__device__ __forceinline__ double div_zero_aware(double x, double y) {
+    if (x == 0.0 && y == y && y != 0.0 && fabs(y) != CUDART_INF) return ((__double_as_longlong(x) ^ __double_as_longlong(y)) < 0) ? -0.0 : 0.0;
+    return x / y;
+}
+
+// Metal, lambertian and isotropic surfaces.  All direction sampling (cosine lobe, uniform sphere, cone towards a sphere
+// light) funnels through ONE sincos + ONE orthonormal-basis site, selected per lane, so the lanes of a warp stay together
+// whatever they sample.
+__device__ __forceinline__ bool shade_surface(const DeviceScene& S, const HitRecord& rec, const Material& M, Ray& ray, d3& beta, d3& L,
+                                              const Rng& rng, uint32_t bounce) {
     const uint32_t block_a = 2u + 2u * bounce, block_b = block_a + 1u;
-
-    if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) {  // material.zig:88-96; no scatter => return emission (render.zig:238-240)
-        // back faces emit 0; the product is still formed so that a NaN/inf throughput poisons the sample as it does in the
-        // reference's recursion (0 * NaN), which the writer later zeroes (writer.zig:72-94)
-        d3 e = rec.front_face ? texture_color(S, M.texture, rec) : mk(0, 0, 0);
-        L = L + beta * e;
-        return false;
-    }
-    if (M.kind == WRT_MAT_DIELECTRIC) {  // material.zig:190-218
-        double index = rec.front_face ? 1.0 / M.param : M.param;
-        d3 in_unit = normalize(ray.d);
-        double cos_theta = fmin(dot(-in_unit, rec.normal), 1.0);
-        double sin_theta = sqrt(1 - cos_theta * cos_theta);
-        double u0, unused;
-        rng_pair(rng, block_a, u0, unused);
-        d3 dir;
-        if (index * sin_theta > 1.0 || reflectance(M.param, cos_theta) > u0) dir = reflect(in_unit, rec.normal);
-        else dir = refract(in_unit, rec.normal, index);
-        ray.o = rec.point;  // attenuation (1,1,1)
-        ray.d = dir;
-        return true;
-    }
-
-    // ---- metal / lambertian / isotropic: choose what to sample -------------------------------------------------
     const bool diffuse = (M.kind != WRT_MAT_METAL);
     int mode = SM_SPHERE_UNIFORM;  // metal fuzz (material.zig:167-168) and the isotropic SpherePdf (pdf.zig:40-42)
     d3 attenuation = mk(M.ar, M.ag, M.ab);
@@ -156,7 +162,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
         }
     }
 
-    // ---- the one sampling site -------------------------------------------------------------------------------------
+    // ---- the one sampling site ----
     double u1, u2;
     rng_pair(rng, block_b, u1, u2);
     d3 dir;
@@ -202,7 +208,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
         return true;
     }
 
-    // ---- diffuse weights: attenuation * scatteringPdf / pdf (render.zig:280-285) -----------------------------------
+    // ---- diffuse weights: attenuation * scatteringPdf / pdf (render.zig:280-285) ----
     const d3 dir_unit = normalize(dir);
     const double surface_pdf = cosine_pdf ? fmax(0.0, dot(dir_unit, w_n) / WRT_PI) : 1.0 / (4.0 * WRT_PI);  // pdf.zig:58-61, 36-38
     double pdf_value = surface_pdf;
@@ -210,10 +216,26 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
     double sp;  // material.scatteringPdf, material.zig:118-125 / 145-150
     if (M.kind == WRT_MAT_LAMBERTIAN) sp = fmax(0.0, dot(rec.normal, dir_unit) / WRT_PI);
     else sp = 1.0 / (4.0 * WRT_PI);
-    beta = (beta * (attenuation * sp)) / pdf_value;
+    d3 w = beta * (attenuation * sp);
+    beta = mk(div_zero_aware(w.x, pdf_value), div_zero_aware(w.y, pdf_value), div_zero_aware(w.z, pdf_value));
     ray.o = rec.point;
     ray.d = dir;
     return true;
+}
+
+// All classes in one call (megakernel).
+__device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstants& rc, const ClosestHit& ch, Ray& ray, d3& beta, d3& L,
+                                      const Rng& rng, uint32_t bounce) {
+    if (ch.pc == WRT_NONE) {  // render.zig:215-217
+        L = L + beta * ld3(rc.background);
+        return false;
+    }
+    HitRecord rec;
+    resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec);
+    const Material M = S.materials[rec.material];
+    if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) return shade_emissive(S, rec, M, beta, L);
+    if (M.kind == WRT_MAT_DIELECTRIC) return shade_dielectric(rec, M, ray, rng, bounce);
+    return shade_surface(S, rec, M, ray, beta, L, rng, bounce);
 }
 
 enum { TRAV_LANE = 0, TRAV_PACKET = 1 };
@@ -422,6 +444,216 @@ cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_
     return cudaGetLastError();
 }
 
+// =============================================================================================================
+// Wavefront engine: the same path integrator as render_kernel, cut into small kernels that meet at
+// queues in HBM.  A pool of path slots — slot = (sample chunk, pixel), the accumulation slot of the resolve pass —
+// each works through its samples one path at a time.  Per iteration:
+//     wf_generate   dead slots with samples left : Sobol jitter + camera ray            -> extend queue
+//     wf_extend     closest hit (packet or per-lane scan); miss => background, finish    -> surface / metal / other queue
+//     wf_shade<Q>   one material class per launch, so every lane of a warp runs the same code
+//                   (surface = lambertian|isotropic, metal, other = dielectric|emissive) -> next extend queue | regenerate queue
+// Queue appends are warp-aggregated (one atomic per warp).  A slot is owned by exactly one thread at any time, so
+// path state and the per-slot colour sums need no atomics and every slot adds its samples in sample order: the
+// frame is bit-identical to render_kernel's.
+// =============================================================================================================
+__device__ __forceinline__ uint32_t* wf_queue(const WavefrontArgs& A, int q) { return A.queues + (size_t)q * A.capacity; }
+
+// warp-aggregated append: one atomicAdd per warp and queue
+__device__ __forceinline__ void wf_push(const WavefrontArgs& A, int q, bool pred, uint32_t slot) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)leader) base = atomicAdd(&A.counters[q], (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) wf_queue(A, q)[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+__device__ __forceinline__ void wf_slot_pixel(const RenderConstants& rc, const WavefrontArgs& A, uint32_t slot, uint32_t& chunk,
+                                              uint32_t& col, uint32_t& row) {
+    chunk = slot / A.n_pixels;
+    const uint32_t local = slot % A.n_pixels;
+    const uint32_t local_row = local / rc.width;
+    col = local % rc.width;
+    row = rc.row_shard_index + local_row * rc.row_shard_count;
+}
+
+// A path ended: add it to the slot's colour sum (render.zig:129-135); the slot goes to the regenerate queue if it has
+// samples left.  Returns whether to push to the regenerate queue (the caller does the warp-wide push).
+__device__ __forceinline__ bool wf_finish_path(const RenderConstants& rc, const WavefrontArgs& A, uint32_t slot, PathState& P, d3 L) {
+    const double scale = 1.0 / (double)rc.spp;
+    double* acc = A.accum + (size_t)slot * 3;
+    acc[0] += L.x * scale; acc[1] += L.y * scale; acc[2] += L.z * scale;
+    const uint32_t chunk = slot / A.n_pixels;
+    const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
+    const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
+    const uint32_t next = P.sample + 1;
+    A.paths[slot].sample = next;
+    if (next < s_last) return true;
+    atomicAdd(&A.counters[10], 1ull);  // this slot is done (once per slot)
+    return false;
+}
+
+// iteration parity selects the extend / regenerate queue pair: kernels of iteration `it` read E[it&1], R[it&1] and write
+// E[(it+1)&1], R[(it+1)&1] (wf_generate appends to E[it&1] before wf_extend drains it).
+__global__ void __launch_bounds__(256) wf_init_kernel(WavefrontArgs A) {
+    const RenderConstants& rc = c_rc;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.capacity; slot += gridDim.x * blockDim.x) {
+        const uint32_t chunk = slot / A.n_pixels;
+        A.paths[slot].sample = rc.sample_begin + chunk * rc.chunk_size;  // first sample of the slot (not yet generated)
+        A.accum[(size_t)slot * 3 + 0] = 0.0; A.accum[(size_t)slot * 3 + 1] = 0.0; A.accum[(size_t)slot * 3 + 2] = 0.0;
+        wf_queue(A, WQ_REGEN0)[slot] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[WQ_REGEN0] = A.capacity;
+}
+
+__global__ void __launch_bounds__(256) wf_generate_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = c_rc;
+    const int q_in = WQ_REGEN0 + (int)parity, q_out = WQ_EXTEND0 + (int)parity;
+    const uint32_t n = (uint32_t)A.counters[q_in];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    Rng rng;
+    rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
+    unsigned long long started = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        if (valid) {
+            slot = wf_queue(A, q_in)[i];
+            uint32_t chunk, col, row;
+            wf_slot_pixel(rc, A, slot, chunk, col, row);
+            const uint32_t s = A.paths[slot].sample;
+            rng.pixel = row * rc.width + col;
+            rng.sample = s;
+            const Ray r = sample_ray(rc, col, row, s, rc.dof != 0, S.has_moving != 0, &rng);
+            PathState P;
+            P.ox = r.o.x; P.oy = r.o.y; P.oz = r.o.z; P.dx = r.d.x; P.dy = r.d.y; P.dz = r.d.z;
+            P.bx = 1.0; P.by = 1.0; P.bz = 1.0; P.lx = 0.0; P.ly = 0.0; P.lz = 0.0;
+            P.t = 0.0; P.hit_pc = WRT_NONE; P.hit_xf = WRT_NONE;
+            P.depth_left = rc.max_depth; P.sample = s; P.time = r.time;
+            A.paths[slot] = P;
+            ++started;
+        }
+        wf_push(A, q_out, valid, slot);
+    }
+    for (int off = 16; off > 0; off >>= 1) started += __shfl_down_sync(0xffffffffu, started, off);
+    if ((threadIdx.x & 31u) == 0 && started) atomicAdd(&A.counters[9], started);
+}
+
+template <int CULL, int TRAV>
+__global__ void __launch_bounds__(128) wf_extend_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = c_rc;
+    const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
+    const uint32_t n = (uint32_t)A.counters[q_in];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n);  // rays = closest-hit queries
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        d3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+        double time = 0.0;
+        if (valid) {
+            slot = wf_queue(A, q_in)[i];
+            const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
+            const double2 a = p[0], b = p[1], c = p[2];
+            o = mk(a.x, a.y, b.x); d = mk(b.y, c.x, c.y);
+            if (S.has_moving) time = A.paths[slot].time;
+        }
+        ClosestHit ch;
+        if (TRAV == TRAV_PACKET) {
+            ch = closest_hit_packet<CULL>(S, valid, o, d, time, 1e-4, CUDART_INF);
+        } else {
+            ch.pc = WRT_NONE; ch.t = CUDART_INF; ch.xform = WRT_NONE;
+            if (valid) ch = closest_hit<CULL>(S, o, d, time, 1e-4, CUDART_INF);
+        }
+        int route = -1;  // shade queue
+        bool regen = false;
+        if (valid) {
+            if (ch.pc == WRT_NONE) {  // miss: L += beta * background, path ends (render.zig:215-217)
+                PathState P = A.paths[slot];
+                d3 L = mk(P.lx, P.ly, P.lz) + mk(P.bx, P.by, P.bz) * ld3(rc.background);
+                regen = wf_finish_path(rc, A, slot, P, L);
+            } else {
+                PathState* P = A.paths + slot;
+                P->t = ch.t; P->hit_pc = ch.pc; P->hit_xf = ch.xform;
+                const uint32_t kind = S.materials[__ldg(&S.ops[ch.pc].z)].kind;
+                route = (kind == WRT_MAT_METAL) ? WQ_METAL : ((kind == WRT_MAT_LAMBERTIAN || kind == WRT_MAT_ISOTROPIC) ? WQ_SURFACE : WQ_OTHER);
+            }
+        }
+        wf_push(A, WQ_SURFACE, route == WQ_SURFACE, slot);
+        wf_push(A, WQ_METAL, route == WQ_METAL, slot);
+        wf_push(A, WQ_OTHER, route == WQ_OTHER, slot);
+        wf_push(A, q_regen, regen, slot);
+    }
+}
+
+template <int QUEUE>
+__global__ void __launch_bounds__(128) wf_shade_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = c_rc;
+    const int q_extend = WQ_EXTEND0 + (int)(parity ^ 1u), q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
+    const uint32_t n = (uint32_t)A.counters[QUEUE];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    Rng rng;
+    rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        bool extend = false, regen = false;
+        if (valid) {
+            slot = wf_queue(A, QUEUE)[i];
+            PathState P = A.paths[slot];
+            uint32_t chunk, col, row;
+            wf_slot_pixel(rc, A, slot, chunk, col, row);
+            rng.pixel = row * rc.width + col;
+            rng.sample = P.sample;
+            Ray ray;
+            ray.o = mk(P.ox, P.oy, P.oz); ray.d = mk(P.dx, P.dy, P.dz); ray.time = P.time;
+            d3 beta = mk(P.bx, P.by, P.bz), L = mk(P.lx, P.ly, P.lz);
+            ClosestHit ch;
+            ch.t = P.t; ch.pc = P.hit_pc; ch.xform = P.hit_xf;
+            HitRecord rec;
+            resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec);
+            const Material M = S.materials[rec.material];
+            const uint32_t bounce = rc.max_depth - P.depth_left;
+            bool cont;
+            if (QUEUE == WQ_OTHER) {
+                if (M.kind == WRT_MAT_DIELECTRIC) cont = shade_dielectric(rec, M, ray, rng, bounce);
+                else cont = shade_emissive(S, rec, M, beta, L);
+            } else {
+                cont = shade_surface(S, rec, M, ray, beta, L, rng, bounce);
+            }
+            const uint32_t depth_left = P.depth_left - 1;
+            if (!cont || depth_left == 0) {
+                if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
+                regen = wf_finish_path(rc, A, slot, P, L);
+            } else {
+                PathState* out = A.paths + slot;
+                double2* w = reinterpret_cast<double2*>(out);
+                w[0] = make_double2(ray.o.x, ray.o.y); w[1] = make_double2(ray.o.z, ray.d.x); w[2] = make_double2(ray.d.y, ray.d.z);
+                if (QUEUE != WQ_OTHER) {  // dielectric attenuation is (1,1,1) and it gathers nothing
+                    w[3] = make_double2(beta.x, beta.y); w[4] = make_double2(beta.z, L.x); w[5] = make_double2(L.y, L.z);
+                }
+                out->depth_left = depth_left;
+                extend = true;
+            }
+        }
+        wf_push(A, q_extend, extend, slot);
+        wf_push(A, q_regen, regen, slot);
+    }
+}
+
+// reset the queues consumed by iteration `parity` so the next iteration can append to them
+__global__ void wf_reset_kernel(WavefrontArgs A, uint32_t parity) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        A.counters[WQ_EXTEND0 + parity] = 0;
+        A.counters[WQ_REGEN0 + parity] = 0;
+        A.counters[WQ_SURFACE] = 0;
+        A.counters[WQ_METAL] = 0;
+        A.counters[WQ_OTHER] = 0;
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------
 template <typename F>
 static cudaError_t dispatch(uint32_t cull_mode, bool packet, F&& f) {
@@ -487,6 +719,24 @@ cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* ind
     if (n == 0) return cudaSuccess;
     uint32_t grid = (uint32_t)((n + 127) / 128 < 4096 ? (n + 127) / 128 : 4096);
     sobol_dimension_kernel<<<grid, 128, 0, stream>>>(matrices, index, dimension, n, owen_fast, seed, out);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_init(const WavefrontArgs& A, uint32_t grid, cudaStream_t stream) {
+    wf_init_kernel<<<grid, 256, 0, stream>>>(A);
+    return cudaGetLastError();
+}
+// One wavefront iteration: generate -> extend -> shade (surface, metal, other) -> reset of the consumed queues.
+cudaError_t wf_launch_iteration(const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
+                                uint32_t grid, cudaStream_t stream) {
+    wf_generate_kernel<<<grid, 256, 0, stream>>>(A, S, parity);
+    dispatch(cull_mode, packet, [&](auto c, auto t) {
+        wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(A, S, parity);
+    });
+    wf_shade_kernel<WQ_SURFACE><<<grid * 2, 128, 0, stream>>>(A, S, parity);
+    wf_shade_kernel<WQ_METAL><<<grid * 2, 128, 0, stream>>>(A, S, parity);
+    wf_shade_kernel<WQ_OTHER><<<grid * 2, 128, 0, stream>>>(A, S, parity);
+    wf_reset_kernel<<<1, 32, 0, stream>>>(A, parity);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,34 @@ struct RenderConstants {
     uint32_t sample_begin, sample_end, chunk_size, n_chunks;
 };
 
+// ---- wavefront engine (wrt_kernels.cu) ----
+struct __align__(16) PathState {  // 128 bytes, one L2 line per slot
+    double ox, oy, oz, dx, dy, dz;  // ray
+    double bx, by, bz;              // throughput
+    double lx, ly, lz;              // radiance gathered by this path
+    double t;                       // closest hit
+    uint32_t hit_pc, hit_xf;
+    uint32_t depth_left, sample;    // `sample` = index of the sample in flight
+    double time;
+};
+static_assert(sizeof(PathState) == 128, "PathState must stay one cache line");
+
+enum { WQ_EXTEND0 = 0, WQ_EXTEND1, WQ_REGEN0, WQ_REGEN1, WQ_SURFACE, WQ_METAL, WQ_OTHER, WQ_COUNT };
+// counters: [0..WQ_COUNT) queue sizes, [8] rays, [9] paths started, [10] slots finished
+
+struct WavefrontArgs {
+    PathState* paths;
+    uint32_t* queues;             // WQ_COUNT arrays of `capacity`
+    unsigned long long* counters; // 16 entries
+    double* accum;                // [slot][3]
+    uint32_t capacity;            // number of slots
+    uint32_t n_pixels;            // pixels of this shard (slot % n_pixels = local pixel)
+};
+
+cudaError_t wf_launch_init(const WavefrontArgs& A, uint32_t grid, cudaStream_t stream);
+cudaError_t wf_launch_iteration(const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
+                                uint32_t grid, cudaStream_t stream);
+
 cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream);
 cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream);
 
