@@ -83,7 +83,6 @@ def scene_images(scene: str):
     import numpy as np
     if scene not in ("earth", "rtw_final", "shrek_quads"):
         return None, None
-    y, x = np.mgrid[0:1024, 0:2048]
     def procedural(name, w, h):
         yy, xx = np.mgrid[0:h, 0:w]
         seed = sum(name.encode())
@@ -260,15 +259,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    distributed = importlib.import_module("zig-weekend-raytracer_b200.distributed")
+
     def gather_frame():
         """NCCL gather of the row shards to rank 0 + interleave into the full frame (N > 1 only)."""
-        if not dist:
-            return
-        dist.gather(d_fb, gather_list, dst=0)
-        if rank == 0:
-            for r in range(world):
-                n_r = (H - r + world - 1) // world
-                d_full[r::world] = gather_list[r][:n_r]
+        if dist:
+            distributed.gather_frame(dist, d_fb, H, rank, world, out=d_full, gather_list=gather_list)
 
     def device_step():
         ctx.render_device(cam, params, d_fb.data_ptr(), LANES * 8)

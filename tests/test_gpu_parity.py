@@ -353,3 +353,87 @@ def test_full_size_cornell_config_properties(ctx, wrt, wro):
     small, _ = sc.render(sc.camera(64, 64), sc.params(64, 64, 256, 50, seed=6), wro.RNG_COUNTER)
     assert abs(np.nanmean(full[..., :3]) - np.nanmean(small[..., :3])) / np.nanmean(small[..., :3]) < 0.03
     sc.close()
+
+
+# ---- engines and traversal variants: all must agree bit for bit ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cornell_box", "emissive", "balls", "rtw_final", "earth", "shrek_quads"])
+def test_wavefront_engine_is_bit_identical_to_megakernel(ctx, wrt, wro, images, name):
+    """Same integrator, two schedules (persistent megakernel vs. path pool + per-material queues): every slot adds its
+    samples in sample order in both, so the frames, ray counts and path counts are identical."""
+    sc = wro.OracleScene(name, seed=1, images=images)
+    ctx.upload_scene(sc.flatten())
+    w, h = 61, 37
+    cam = sc.camera(w, h)
+    for cull in (wrt.WRT_CULL_TIGHT, wrt.WRT_CULL_REFERENCE):
+        a = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_MEGAKERNEL))
+        sa = ctx.stats()
+        b = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_WAVEFRONT))
+        sb = ctx.stats()
+        np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert (sa.rays, sa.paths) == (sb.rays, sb.paths)
+        assert sb.kernel_launches > sa.kernel_launches
+    sc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "balls", "rtw_final", "synthetic"])
+def test_packet_and_lane_traversals_agree(ctx, wrt, wro, images, name):
+    """The warp-uniform packet scan and the per-lane scan are the same sequential closest-hit search: forcing either on
+    any scene gives identical hits (ids and t bits) and identical frames."""
+    sc = wro.OracleScene(name, seed=1, n_prims=2048, images=images)
+    ctx.upload_scene(sc.flatten())
+    rng = np.random.default_rng(3)
+    n = 4000
+    span = {"cornell_box": (0, 555), "balls": (-12, 12), "rtw_final": (-200, 600), "synthetic": (-1000, 1000)}[name]
+    o = rng.uniform(span[0], span[1], (n, 3))
+    d = rng.normal(size=(n, 3))
+    for cull in (wrt.WRT_CULL_TIGHT, wrt.WRT_CULL_REFERENCE):
+        lane = ctx.trace_rays(o, d, cull_mode=cull | wrt.WRT_TRAV_FORCE_LANE)
+        packet = ctx.trace_rays(o, d, cull_mode=cull | wrt.WRT_TRAV_FORCE_PACKET)
+        np.testing.assert_array_equal(lane["prim_id"], packet["prim_id"])
+        np.testing.assert_array_equal(lane["t"].view(np.uint64), packet["t"].view(np.uint64))
+        np.testing.assert_array_equal(lane["normal"].view(np.uint64), packet["normal"].view(np.uint64))
+    w, h = 40, 30
+    cam = sc.camera(w, h)
+    a = ctx.render(cam, sc.params(w, h, 4, 12, seed=2, flags=wrt.WRT_FLAG_FORCE_LANE))
+    b = ctx.render(cam, sc.params(w, h, 4, 12, seed=2, flags=wrt.WRT_FLAG_FORCE_PACKET))
+    np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64))
+    sc.close()
+
+
+def test_host_mirror_scene_draw_end_to_end(wrt, wro, images):
+    """Scene.draw -> Renderer.render of the C++ host mirror (flatten + wrt_upload_scene + wrt_render) against the oracle."""
+    import importlib
+    host = importlib.import_module("zig-weekend-raytracer_b200.host")
+    hs = host.HostScene("cornell_box")
+    fb, st = hs.draw(48, 48, 8, 20, seed=9, cull_mode=wrt.WRT_CULL_TIGHT)
+    sc = wro.OracleScene("cornell_box")
+    want, so = sc.render(sc.camera(48, 48), sc.params(48, 48, 8, 20, seed=9), wro.RNG_COUNTER)
+    assert st["rays"] == so.rays and st["paths"] == so.paths
+    assert mae(fb[..., :3], want[..., :3]) <= 1e-12
+    hs.close(); sc.close()
+
+
+def test_cli_renders_a_ppm(wrt, wro, tmp_path):
+    """`weekend-raytracer` with the reference's flags (README.md:36) writes the PPM the reference writer would write for
+    the same frame."""
+    import importlib
+    import subprocess
+    host = importlib.import_module("zig-weekend-raytracer_b200.host")
+    out = tmp_path / "image.ppm"
+    r = subprocess.run([str(host.CLI_PATH), "--image_width=40", "--image_height=30", "--ray_bounce_max_depth=10",
+                        "--thread_pool_size=4", "--samples_per_pixel=8", f"--image_out_path={out}", "--seed=1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for msg in ("scene initialized", "scene rendered", "scene written to file"):  # main.zig:94,97,105
+        assert msg in r.stderr
+    raw = out.read_bytes()
+    assert raw.startswith(b"P3\n40 30\n255\n") and len(raw) == 40 * 30 * 12 + len(b"P3\n40 30\n255\n")
+    sc = wro.OracleScene("emissive")  # the default scene (main.zig:25)
+    want, _ = sc.render(sc.camera(40, 30), sc.params(40, 30, 8, 10, seed=1), wro.RNG_COUNTER)
+    rgb = wro.encode_image(want)
+    body = "".join(f"{a} {b} {c}\n" for a, b, c in rgb.reshape(-1, 3)).encode()
+    got = raw[len(b"P3\n40 30\n255\n"):].rstrip(b"\0")
+    # device libm may differ from glibc by an ulp in a channel right at a quantisation step: allow a handful of lines
+    diff = sum(1 for x, y in zip(got.split(b"\n"), body.split(b"\n")) if x != y)
+    assert diff <= 3
+    sc.close()

@@ -393,9 +393,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
     const uint64_t resident_warps = (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
-    // Engine: the wavefront (queues in HBM, one small kernel per stage) wins as soon as there is enough work to fill its
-    // path pool; the persistent megakernel serves small renders and the degenerate depth-0 frame.
-    bool wavefront = (uint64_t)n_pixels64 * n_samples >= (1ull << 20) && p.max_ray_bounce_depth > 0;
+    // Engine: the persistent megakernel is the default — on the measured configs it matches the
+    // wavefront (queues in HBM, one small kernel per stage) without its state traffic; the wavefront is selected by flag.
+    bool wavefront = false;
     if (p.flags & WRT_FLAG_ENGINE_MEGAKERNEL) wavefront = false;
     if ((p.flags & WRT_FLAG_ENGINE_WAVEFRONT) && p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0) wavefront = true;
     uint32_t n_chunks = 1;

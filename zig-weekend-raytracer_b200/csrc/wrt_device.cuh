@@ -35,8 +35,9 @@ enum OpKind : uint32_t {
 struct __align__(16) BoxRef {   // the reference's cached AABB.min/max, x and y only (aabb.zig:80-101 as executed)
     double min_x, min_y, max_x, max_y;
 };
-struct __align__(16) BoxTight { // recomputed conservative box, slab pairs
-    double2 x, y, z;            // (min,max) per axis
+struct __align__(16) BoxTight { // recomputed conservative box in binary32, rounded outwards and padded (wrt_program.cu)
+    float min_x, min_y, min_z, _p0;
+    float max_x, max_y, max_z, _p1;
 };
 struct __align__(16) SphereGeom { // entity.zig:536-537
     double cx, cy, cz, radius;
@@ -292,30 +293,40 @@ struct Culler<WRT_CULL_REFERENCE> {
     }
 };
 
-// Fast path: proper 3-axis slab intersection on recomputed, padded boxes with a per-ray reciprocal direction.
-// Culling only has to be conservative, so this is the one place that uses FMA.
+// Fast path: proper 3-axis slab intersection on boxes recomputed from the primitives.  Culling only has to be
+// conservative, never exact, so it runs in binary32 on the full-rate FP32 pipe (the FP64 pipe has half the lanes and no
+// single-instruction min/max): boxes are rounded outwards and padded at upload, the ray carries an absolute error bound
+// per axis, and the exit distance gets a relative slack.  Error budget: inv = fl(1/fl(d)) is off by
+// <= 3 ulp, o*inv and the FMA round once each, so a slab distance is off by <= (|o*inv| + |b*inv|) * 2^-22 + |t| * 2^-21.
 template <>
 struct Culler<WRT_CULL_TIGHT> {
-    d3 inv, oi;  // 1/d and o/d
-    // A zero (or denormal-small) direction component would make inv infinite and b*inv - o*inv an inf - inf NaN that
-    // loses the sign of (b - o); nudging it to +-1e-200 keeps every slab bound finite and correctly signed.
-    static __device__ __forceinline__ double safe_inv(double v) {
-        return 1.0 / (fabs(v) < 1e-200 ? copysign(1e-200, v) : v);
+    float inv_x, inv_y, inv_z;   // 1 / d
+    float oi_x, oi_y, oi_z;      // o / d
+    float err_x, err_y, err_z;   // |o / d| * 2^-21: absolute slab-distance error of this ray, per axis
+    static __device__ __forceinline__ float safe_inv(double v) {
+        float f = (float)v;
+        // a zero / denormal component would make inv infinite and b*inv - o*inv an inf - inf NaN
+        if (!(fabsf(f) >= 1e-20f)) f = copysignf(1e-20f, __double2hiint(v) < 0 ? -1.0f : 1.0f);
+        return __frcp_rn(f);
     }
     __device__ __forceinline__ void set_ray(d3 ro, d3 rd) {
-        inv = mk(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
-        oi = mk(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+        inv_x = safe_inv(rd.x); inv_y = safe_inv(rd.y); inv_z = safe_inv(rd.z);
+        oi_x = (float)ro.x * inv_x; oi_y = (float)ro.y * inv_y; oi_z = (float)ro.z * inv_z;
+        err_x = fabsf(oi_x) * 4.8e-7f; err_y = fabsf(oi_y) * 4.8e-7f; err_z = fabsf(oi_z) * 4.8e-7f;
     }
     __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
-        const double2* p = reinterpret_cast<const double2*>(S.boxes_tight + box);
-        double2 bx = __ldg(p), by = __ldg(p + 1), bz = __ldg(p + 2);
-        double t0x = fma(bx.x, inv.x, -oi.x), t1x = fma(bx.y, inv.x, -oi.x);
-        double t0y = fma(by.x, inv.y, -oi.y), t1y = fma(by.y, inv.y, -oi.y);
-        double t0z = fma(bz.x, inv.z, -oi.z), t1z = fma(bz.y, inv.z, -oi.z);
-        // fmin/fmax drop NaNs (0 * inf), which can only widen the interval
-        double lo = fmax(fmax(fmin(t0x, t1x), fmin(t0y, t1y)), fmax(fmin(t0z, t1z), tmin));
-        double hi = fmin(fmin(fmax(t0x, t1x), fmax(t0y, t1y)), fmin(fmax(t0z, t1z), tmax));
-        return hi * 1.0000000000000004 >= lo;
+        const float4* p = reinterpret_cast<const float4*>(S.boxes_tight + box);
+        const float4 lo4 = __ldg(p), hi4 = __ldg(p + 1);  // (min.x, min.y, min.z, -), (max.x, max.y, max.z, -)
+        const float ax = fmaf(lo4.x, inv_x, -oi_x), bx = fmaf(hi4.x, inv_x, -oi_x);
+        const float ay = fmaf(lo4.y, inv_y, -oi_y), by = fmaf(hi4.y, inv_y, -oi_y);
+        const float az = fmaf(lo4.z, inv_z, -oi_z), bz = fmaf(hi4.z, inv_z, -oi_z);
+        const float nx = fminf(ax, bx) - err_x, fx = fmaxf(ax, bx) + err_x;
+        const float ny = fminf(ay, by) - err_y, fy = fmaxf(ay, by) + err_y;
+        const float nz = fminf(az, bz) - err_z, fz = fmaxf(az, bz) + err_z;
+        const float t_lo = __double2float_rd(tmin), t_hi = __double2float_ru(tmax);
+        const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
+        const float hi = fminf(fminf(fx, fy), fminf(fz, t_hi));
+        return hi * 1.000002f + 1e-30f >= lo;  // relative slack for the rounding of inv (|t| * 2^-21 on either side)
     }
 };
 

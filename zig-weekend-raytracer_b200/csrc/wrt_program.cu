@@ -131,18 +131,32 @@ struct Compiler {
         return true;
     }
 
+    // binary32 box for the FP32 culler: padded by 4e-6 of the coordinate magnitude (covers |b*inv| * 2^-22 and the
+    // binary64 rounding of the primitives' own arithmetic) and rounded outwards.
+    static float round_down(double v) {
+        float f = (float)v;
+        return ((double)f > v) ? std::nextafterf(f, -std::numeric_limits<float>::infinity()) : f;
+    }
+    static float round_up(double v) {
+        float f = (float)v;
+        return ((double)f < v) ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f;
+    }
     static BoxTight padded(const Box3& b) {
         BoxTight t;
+        t._p0 = t._p1 = 0.0f;
         if (!b.valid()) {  // empty subtree: a box nothing can hit
-            t.x = make_double2(1.0, -1.0); t.y = t.x; t.z = t.x;
+            t.min_x = t.min_y = t.min_z = 1.0f;
+            t.max_x = t.max_y = t.max_z = -1.0f;
             return t;
         }
-        double mag = 1.0;
-        for (int k = 0; k < 3; ++k) mag = std::max(mag, std::max(std::fabs(b.mn[k]), std::fabs(b.mx[k])));
-        const double pad = mag * 1e-7;  // >> binary64 rounding of the slab arithmetic, << any scene feature
-        t.x = make_double2(b.mn[0] - pad, b.mx[0] + pad);
-        t.y = make_double2(b.mn[1] - pad, b.mx[1] + pad);
-        t.z = make_double2(b.mn[2] - pad, b.mx[2] + pad);
+        double lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            const double mag = std::max(1.0, std::max(std::fabs(b.mn[k]), std::fabs(b.mx[k])));
+            lo[k] = b.mn[k] - mag * 4e-6;
+            hi[k] = b.mx[k] + mag * 4e-6;
+        }
+        t.min_x = round_down(lo[0]); t.min_y = round_down(lo[1]); t.min_z = round_down(lo[2]);
+        t.max_x = round_up(hi[0]); t.max_y = round_up(hi[1]); t.max_z = round_up(hi[2]);
         return t;
     }
 
