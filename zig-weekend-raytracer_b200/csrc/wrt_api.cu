@@ -98,6 +98,7 @@ struct wrt_ctx {
     DevBuf<wrt::ImageDesc> d_images;
     DevBuf<wrt::Light> d_lights;
     DevBuf<uint32_t> d_sobol_matrices;
+    DevBuf<wrt::SobolLut> d_sobol_lut;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
 
@@ -195,7 +196,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->free_images();
     ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
-    ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release();
+    ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
     ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_counters.release();
     if (ctx->h_wf_counters) cudaFreeHost(ctx->h_wf_counters);
@@ -317,6 +318,34 @@ static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
     }
     std::memcpy(t.dim0, ctx->blob.matrices32, sizeof t.dim0);
     std::memcpy(t.dim1, ctx->blob.matrices32 + 52, sizeof t.dim1);
+    for (int i = 0; i < 52; ++i)  // the device evaluates dimension 0 as a bit reversal
+        if (t.dim0[i] != (i < 32 ? (0x80000000u >> i) : 0u)) return ctx->fail(WRT_E_INVALID, "Sobol dimension 0 is not van der Corput");
+    // byte-indexed folds of the three matrices (wrt_device.cuh: SobolLut)
+    std::vector<wrt::SobolLut> lut(1);
+    std::memset(lut.data(), 0, sizeof(wrt::SobolLut));
+    for (int k = 0; k < 7; ++k)
+        for (int v = 0; v < 256; ++v) {
+            uint64_t inv = 0, vd = 0;
+            uint32_t d1 = 0;
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * k + j;
+                if (!((v >> j) & 1) || col >= 52) continue;
+                inv ^= t.vdc_inv[col];
+                vd ^= t.vdc[col];
+                d1 ^= t.dim1[col];
+            }
+            lut[0].vdc_inv[k][v] = inv;
+            lut[0].dim1[k][v] = d1;
+            if (k < 2) lut[0].vdc[k][v] = vd;
+        }
+    // b = (px << m | py) ^ delta: delta is an XOR of VdC rows; find how many bytes can be non-zero
+    uint64_t b_mask = ((uint64_t)1 << (2 * t.log2_scale)) - 1;
+    for (int c = 0; c < 52; ++c) b_mask |= t.vdc[c];
+    t.b_bytes = 0;
+    while (t.b_bytes < 8 && (b_mask >> (8 * t.b_bytes)) != 0) ++t.b_bytes;
+    if (t.b_bytes > 7) return ctx->fail(WRT_E_LIMIT, "Sobol index exceeds 56 bits");
+    CU(ctx->d_sobol_lut.upload(lut, ctx->stream));
+    t.lut = ctx->d_sobol_lut.p;
     CU(wrt::upload_sobol_tables(t, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->sobol_w = width; ctx->sobol_h = height;

@@ -91,12 +91,19 @@ struct DeviceScene {
     uint32_t n_ops, n_lights, has_lights, has_moving;
 };
 
+struct SobolLut {                  // byte-indexed folds of the matrices below (global memory, L1 resident, 23 KB)
+    uint64_t vdc[2][256];          // XOR of VdC[m-1][8k + j] over the set bits j of byte k of the sample index
+    uint64_t vdc_inv[7][256];      // same for VdCInv[m-1] over the bytes of b
+    uint32_t dim1[7][256];         // same for SobolMatrices32[52 + ...] over the bytes of the Sobol index
+};
 struct SobolTables {               // live part of sobolmatrices.zig for one resolution
     uint64_t vdc[52];              // VdCSobolMatrices[m-1]
     uint64_t vdc_inv[52];          // VdCSobolMatricesInv[m-1]
     uint32_t dim0[52];             // SobolMatrices32[0*52 ..]
     uint32_t dim1[52];             // SobolMatrices32[1*52 ..]
     uint32_t log2_scale, scale;
+    uint32_t b_bytes, _pad;        // bytes of b = (px << m | py) ^ delta that can be non-zero
+    const SobolLut* lut;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -186,16 +193,23 @@ __device__ __forceinline__ uint32_t pick_index(double u, uint32_t n) {  // intRa
 // ---------------------------------------------------------------------------------------------------------
 // Sobol pixel sampling (sampler.zig:197-201, 222-234, 249-264, 267-298) — bit exact
 // ---------------------------------------------------------------------------------------------------------
+// The XOR-of-matrix-columns loops of the reference (one iteration per index bit) are GF(2) matrix-vector products;
+// SobolLut holds the same matrices folded into byte-indexed tables (built per resolution at upload), so a product is
+// one lookup per index byte instead of eight predicated XORs.  Results are identical bit for bit (XOR is linear).
 __device__ __forceinline__ uint64_t sobol_interval_to_index(const SobolTables& T, uint64_t sample_idx, uint32_t px, uint32_t py) {
     const uint32_t m = T.log2_scale;
     if (m == 0) return sample_idx;
+    const SobolLut* __restrict__ L = T.lut;
     uint64_t index = sample_idx << (m << 1);
-    uint64_t delta = 0;
-    for (uint32_t c = 0; sample_idx > 0; sample_idx >>= 1, ++c)
-        if (sample_idx & 1) delta ^= T.vdc[c];
-    uint64_t b = ((((uint64_t)px) << m) | (uint64_t)py) ^ delta;
-    for (uint32_t c = 0; b > 0; b >>= 1, ++c)
-        if (b & 1) index ^= T.vdc_inv[c];
+    uint64_t delta = __ldg(&L->vdc[0][sample_idx & 255u]) ^ __ldg(&L->vdc[1][(sample_idx >> 8) & 255u]);
+    uint64_t rest = sample_idx >> 16;  // more than 65535 samples per pixel: finish bit by bit (sampler.zig:279-286)
+    for (uint32_t c = 16; rest > 0; rest >>= 1, ++c)
+        if (rest & 1) delta ^= T.vdc[c];
+    const uint64_t b = ((((uint64_t)px) << m) | (uint64_t)py) ^ delta;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if (k < (int)T.b_bytes) index ^= __ldg(&L->vdc_inv[k][(b >> (8 * k)) & 255u]);  // T.b_bytes is warp-uniform
+    }
     return index;
 }
 __device__ __forceinline__ float sobol_sample_bits_to_float(uint32_t v) {
@@ -203,11 +217,13 @@ __device__ __forceinline__ float sobol_sample_bits_to_float(uint32_t v) {
     return fminf(__fmul_rn(vf, 0x1p-32f), 0x1.fffffep-1f);  // sampler.zig:262-263
 }
 __device__ __forceinline__ void sobol_pixel_2d(const SobolTables& T, uint64_t index, uint32_t px, uint32_t py, double& ox, double& oy) {
-    uint32_t v0 = 0, v1 = 0;
-    uint64_t a = index;
-    for (uint32_t i = 0; a != 0; a >>= 1, ++i) {
-        if (a & 1) { v0 ^= T.dim0[i]; v1 ^= T.dim1[i]; }
-    }
+    // dimension 0 is the van der Corput sequence: its matrix is the bit reversal of the low 32 index bits
+    // (SobolMatrices32[i] = 0x80000000 >> i for i < 32, 0 above; checked when the tables are loaded)
+    const uint32_t v0 = __brev((uint32_t)index);
+    const SobolLut* __restrict__ L = T.lut;
+    uint32_t v1 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v1 ^= __ldg(&L->dim1[k][(index >> (8 * k)) & 255u]);
     const double one_minus_eps = (double)0x1.fffffep-1f;
     double rx = (double)sobol_sample_bits_to_float(v0) * (double)T.scale - (double)px;
     double ry = (double)sobol_sample_bits_to_float(v1) * (double)T.scale - (double)py;
@@ -330,6 +346,15 @@ struct Culler<WRT_CULL_TIGHT> {
     }
 };
 
+// x / y where x == 0 is frequent: a bounce ray leaving an axis-aligned wall has a numerator of exactly 0 against that
+// wall's plane, and a light-sampled direction below the horizon zeroes the throughput (the reference keeps tracing such
+// paths).  IEEE gives +-0 for finite non-zero y, but nvcc's division sends a zero numerator down its ~100-instruction
+// slow path (6 % of all executed instructions before this).  Same result bits, none of the cost.
+__device__ __forceinline__ double div_zero_aware(double x, double y) {
+    if (x == 0.0 && y == y && y != 0.0 && fabs(y) != CUDART_INF) return ((__double_as_longlong(x) ^ __double_as_longlong(y)) < 0) ? -0.0 : 0.0;
+    return x / y;
+}
+
 struct ClosestHit {
     double t;
     uint32_t pc;     // op index of the winning primitive, WRT_NONE = miss
@@ -386,7 +411,7 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
             d3 n = mk(n0.x, n0.y, n1.x);
             double denom = dot(n, d);
             if (!(fabs(denom) < 1e-8)) {
-                double t = (n1.y - dot(n, o)) / denom;
+                double t = div_zero_aware(n1.y - dot(n, o), denom);
                 if ((tmin <= t) && (t <= best.t)) {
                     double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
                     double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
@@ -478,7 +503,7 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
                 d3 n = mk(n0.x, n0.y, n1.x);
                 double denom = dot(n, d);
                 if (!(fabs(denom) < 1e-8)) {
-                    double t = (n1.y - dot(n, o)) / denom;
+                    double t = div_zero_aware(n1.y - dot(n, o), denom);
                     if ((tmin <= t) && (t <= best.t)) {
                         double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
                         double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
@@ -622,7 +647,7 @@ __device__ inline double light_pdf_value_one(const DeviceScene& S, const Light L
         d3 n = mk(q.nx, q.ny, q.nz);
         double denom = dot(n, direction);
         if (fabs(denom) < 1e-8) return 0.0;
-        double t = (q.offset - dot(n, origin)) / denom;
+        double t = div_zero_aware(q.offset - dot(n, origin), denom);
         if (!((1e-3 <= t) && (t <= CUDART_INF))) return 0.0;
         d3 p = origin + direction * t;
         d3 planar = p - mk(q.sx, q.sy, q.sz);

@@ -114,14 +114,6 @@ __device__ __forceinline__ bool shade_dielectric(const HitRecord& rec, const Mat
     return true;
 }
 
-// x / y where x == 0 is frequent (a light-sampled direction below the horizon zeroes the throughput, and the reference keeps
-// tracing that path): IEEE gives +-0 for finite non-zero y, and nvcc's division sends a zero numerator down its ~100
-// instruction slow path.  Same result bits, none of the cost.
-__device__ __forceinline__ double div_zero_aware(double x, double y) {
-    if (x == 0.0 && y == y && y != 0.0 && fabs(y) != CUDART_INF) return ((__double_as_longlong(x) ^ __double_as_longlong(y)) < 0) ? -0.0 : 0.0;
-    return x / y;
-}
-
 // Metal, lambertian and isotropic surfaces.  All direction sampling (cosine lobe, uniform sphere, cone towards a sphere
 // light) funnels through ONE sincos + ONE orthonormal-basis site, selected per lane, so the lanes of a warp stay together
 // whatever they sample.
