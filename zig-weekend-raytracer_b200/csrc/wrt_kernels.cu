@@ -319,6 +319,107 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, WRT_RENDER_MIN_BLOCKS) rende
     }
 }
 
+// Phase-synchronous variant of render_kernel: ONE block of 16 warps per SM, and all 16 warps move through the three phases
+// of an iteration (regenerate | closest hit | shade) together, separated by block barriers.  The integrator is the same,
+// the arithmetic is the same, the frame is bit-identical; what changes is the instruction working set: at any time the
+// whole SM executes one phase (~1-2 K instructions) instead of 16 warps spread over the ~60 KB loop body, which is what
+// made instruction fetch the top stall reason of render_kernel (profiles/README.md).  A warp that finishes its job
+// fetches the next one inside the same loop, so the barrier count per warp stays uniform.
+template <int CULL, int TRAV>
+__global__ void __launch_bounds__(WRT_SYNC_BLOCK, 1) render_kernel_sync(DeviceScene S, double* __restrict__ accum,
+                                                                        unsigned long long* __restrict__ counters) {
+    const RenderConstants& rc = c_rc;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long n_rays = 0, n_paths = 0;
+    const double scale = 1.0 / (double)rc.spp;
+    const bool dof = rc.dof != 0;
+    const bool need_time = S.has_moving != 0;
+    Rng rng;
+    rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
+    rng.pixel = 0; rng.sample = 0;
+
+    bool have_job = false, out_of_jobs = false;
+    uint32_t chunk = 0, local_row = 0, col = 0, row = 0, s = 0, s_last = 0;
+    bool lane_active = false, alive = false;
+    uint32_t depth_left = 0;
+    d3 color = mk(0, 0, 0);
+    Ray ray;
+    ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
+    d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
+
+    for (;;) {
+        // ---- job management + phase A: regenerate ----
+        if (!have_job && !out_of_jobs) {
+            unsigned long long job = 0;
+            if (lane == 0) job = atomicAdd(&counters[0], 1ull);
+            job = __shfl_sync(0xffffffffu, job, 0);
+            if (job >= rc.total_jobs) {
+                out_of_jobs = true;
+            } else {
+                const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
+                chunk = (uint32_t)(job / blocks_per_chunk);
+                const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
+                local_row = rem / rc.n_col_blocks;
+                col = (rem % rc.n_col_blocks) * 32u + lane;
+                row = rc.row_shard_index + local_row * rc.row_shard_count;
+                s = rc.sample_begin + chunk * rc.chunk_size;
+                s_last = min(s + rc.chunk_size, rc.sample_end);
+                lane_active = col < rc.width;
+                color = mk(0, 0, 0);
+                alive = false;
+                rng.pixel = row * rc.width + col;
+                have_job = true;
+            }
+        }
+        if (have_job && !alive && lane_active && s < s_last) {
+            rng.sample = s;
+            ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
+            beta = mk(1, 1, 1); L = mk(0, 0, 0);
+            depth_left = rc.max_depth;
+            alive = depth_left > 0;
+            ++n_paths;
+            if (!alive) ++s;
+        }
+        __syncthreads();
+        // ---- phase B: closest hit ----
+        ClosestHit ch;
+        ch.pc = WRT_NONE; ch.t = CUDART_INF; ch.xform = WRT_NONE;
+        if (__any_sync(0xffffffffu, alive)) {
+            if (TRAV == TRAV_PACKET) ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+            else if (alive) ch = closest_hit<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+        }
+        __syncthreads();
+        // ---- phase C: shade, path end, job end ----
+        if (alive) {
+            ++n_rays;
+            const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
+            --depth_left;
+            if (!cont || depth_left == 0) {
+                if (cont) L = L + beta * 0.0;
+                color = color + L * scale;
+                alive = false;
+                ++s;
+            }
+        }
+        if (have_job && !__any_sync(0xffffffffu, alive || (lane_active && s < s_last))) {
+            if (lane_active) {
+                double* slot = accum + ((size_t)chunk * rc.n_rows_local * rc.width + (size_t)local_row * rc.width + col) * 3;
+                slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
+            }
+            have_job = false;
+        }
+        if (__syncthreads_and(out_of_jobs && !have_job)) break;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
+        n_paths += __shfl_down_sync(0xffffffffu, n_paths, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[1], n_rays);
+        atomicAdd(&counters[2], n_paths);
+    }
+}
+
 // Final pass: framebuffer[pixel] = (clear | previous contents) + sum over chunks in order; optional RGB8.
 __global__ void resolve_kernel(const double* __restrict__ accum, uint32_t n_chunks, uint32_t n_pixels, double clear_r,
                                double clear_g, double clear_b, int no_clear, double* __restrict__ fb, uint32_t stride_doubles,
@@ -663,6 +764,12 @@ cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet,
                           cudaStream_t stream) {
     return dispatch(cull_mode, packet, [&](auto c, auto t) {
         render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+    });
+}
+cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
+                               unsigned long long* counters, cudaStream_t stream) {
+    return dispatch(cull_mode, packet, [&](auto c, auto t) {
+        render_kernel_sync<decltype(c)::value, decltype(t)::value><<<grid, WRT_SYNC_BLOCK, 0, stream>>>(S, accum, counters);
     });
 }
 cudaError_t render_occupancy(uint32_t cull_mode, bool packet, int* blocks_per_sm) {
