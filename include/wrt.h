@@ -211,6 +211,7 @@ typedef struct wrt_stats {
     uint32_t program_ops;    /* size of the compiled traversal program */
     uint32_t n_prims;        /* leaf primitives in DFS order */
     uint32_t _pad;
+    uint64_t traversal_steps;/* node records + ops visited by the per-lane ordered traversal (0 for the packet scan) */
 } wrt_stats;
 
 typedef struct wrt_ctx wrt_ctx;

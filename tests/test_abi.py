@@ -56,7 +56,7 @@ def test_ctypes_mirror_matches_c_layout(wrt, tmp_path):
                                     "clear_color", "seed", "row_shard_index", "row_shard_count", "sample_begin", "sample_end",
                                     "cull_mode", "flags"]),
         "wrt_stats": (wrt.Stats, ["paths", "rays", "render_ms", "kernel_ms", "upload_ms", "kernel_launches", "program_ops",
-                                  "n_prims"]),
+                                  "n_prims", "traversal_steps"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, (_, fields) in structs.items():

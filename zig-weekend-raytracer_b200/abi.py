@@ -85,4 +85,4 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("render_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("kernel_launches", C.c_uint32), ("program_ops", C.c_uint32),
-                ("n_prims", C.c_uint32), ("_pad", C.c_uint32)]
+                ("n_prims", C.c_uint32), ("_pad", C.c_uint32), ("traversal_steps", C.c_uint64)]

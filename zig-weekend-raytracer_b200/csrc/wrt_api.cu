@@ -88,6 +88,7 @@ struct wrt_ctx {
     DevBuf<uint4> d_ops;
     DevBuf<wrt::BoxRef> d_boxes_ref;
     DevBuf<wrt::BoxTight> d_boxes_tight;
+    DevBuf<wrt::Node2> d_nodes2;
     DevBuf<wrt::SphereGeom> d_spheres;
     DevBuf<wrt::SphereAux> d_sphere_aux;
     DevBuf<wrt::QuadGeom> d_quads;
@@ -194,7 +195,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->free_images();
-    ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_spheres.release();
+    ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
@@ -277,6 +278,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     CU(ctx->d_ops.upload(cs.ops, ctx->stream));
     CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
     CU(ctx->d_boxes_tight.upload(cs.boxes_tight, ctx->stream));
+    CU(ctx->d_nodes2.upload(cs.nodes2, ctx->stream));
     CU(ctx->d_spheres.upload(cs.spheres, ctx->stream));
     CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
     CU(ctx->d_quads.upload(cs.quads, ctx->stream));
@@ -287,7 +289,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     CU(ctx->d_lights.upload(cs.lights, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     wrt::DeviceScene& ds = ctx->ds;
-    ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p;
+    ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p; ds.nodes2 = ctx->d_nodes2.p;
     ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
     ds.xforms = ctx->d_xforms.p; ds.xform_chains = ctx->d_xform_chains.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
     ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p;
@@ -295,6 +297,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     ds.n_lights = (uint32_t)cs.lights.size();
     ds.has_lights = cs.has_lights ? 1u : 0u;
     ds.has_moving = cs.has_moving ? 1u : 0u;
+    ds.use_ordered = (cs.max_nesting + 8 <= WRT_STACK_DEPTH) ? 1u : 0u;
     ctx->have_scene = true;
     ctx->stats.program_ops = ds.n_ops;
     ctx->stats.n_prims = cs.n_prims;
@@ -417,7 +420,7 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     // chosen so that the persistent grid has >= 16 jobs per resident warp to balance uneven path lengths.
     int blocks_per_sm = 0;
     const bool packet = use_packet(ctx, p.flags);
-    CU(wrt::render_occupancy(p.cull_mode, packet, &blocks_per_sm));
+    CU(wrt::render_occupancy(ctx->ds, p.cull_mode, packet, &blocks_per_sm));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const bool sync_engine = (p.flags & WRT_FLAG_ENGINE_SYNC) != 0;
     const uint32_t grid = sync_engine ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
@@ -515,6 +518,7 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     CU(cudaEventElapsedTime(&ms_kernel, ctx->ev[1], ctx->ev[2]));
     ctx->stats.rays = wavefront ? wf_rays : counters[1];
     ctx->stats.paths = wavefront ? wf_paths : counters[2];
+    ctx->stats.traversal_steps = wavefront ? 0 : counters[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;
     ctx->stats.kernel_launches = launches;

@@ -39,6 +39,15 @@ struct __align__(16) BoxTight { // recomputed conservative box in binary32, roun
     float min_x, min_y, min_z, _p0;
     float max_x, max_y, max_z, _p1;
 };
+// Child-pair record of a bvh_node (one 64-byte line): both children's binary32 boxes plus where each child lives in the
+// program.  desc: bit 31 set = the child is itself a bvh_node, low bits = its record index; otherwise desc = first op of the
+// child's op range and *_end = one past its last op.  r_desc == WRT_NONE: single-child node (span == 1, entity.zig:231-233).
+struct __align__(16) Node2 {
+    float lmin[3]; uint32_t l_desc;
+    float lmax[3]; uint32_t l_end;
+    float rmin[3]; uint32_t r_desc;
+    float rmax[3]; uint32_t r_end;
+};
 struct __align__(16) SphereGeom { // entity.zig:536-537
     double cx, cy, cz, radius;
 };
@@ -79,6 +88,7 @@ struct DeviceScene {
     const uint4* ops;
     const BoxRef* boxes_ref;
     const BoxTight* boxes_tight;
+    const Node2* nodes2;
     const SphereGeom* spheres;
     const SphereAux* sphere_aux;
     const QuadGeom* quads;
@@ -89,6 +99,7 @@ struct DeviceScene {
     const ImageDesc* images;
     const Light* lights;
     uint32_t n_ops, n_lights, has_lights, has_moving;
+    uint32_t use_ordered, _pad0, _pad1, _pad2;  // ordered traversal allowed (tree depth fits WRT_STACK_DEPTH)
 };
 
 struct SobolLut {                  // byte-indexed folds of the matrices below (global memory, L1 resident, 23 KB)
@@ -344,6 +355,20 @@ struct Culler<WRT_CULL_TIGHT> {
         const float hi = fminf(fminf(fx, fy), fminf(fz, t_hi));
         return hi * 1.000002f + 1e-30f >= lo;  // relative slack for the rounding of inv (|t| * 2^-21 on either side)
     }
+    // same test on an explicit box; also returns the (conservative) entry distance for near-first ordering
+    __device__ __forceinline__ bool entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float t_lo, float t_hi,
+                                          float& t_entry) const {
+        const float ax = fmaf(mnx, inv_x, -oi_x), bx = fmaf(mxx, inv_x, -oi_x);
+        const float ay = fmaf(mny, inv_y, -oi_y), by = fmaf(mxy, inv_y, -oi_y);
+        const float az = fmaf(mnz, inv_z, -oi_z), bz = fmaf(mxz, inv_z, -oi_z);
+        const float nx = fminf(ax, bx) - err_x, fx = fmaxf(ax, bx) + err_x;
+        const float ny = fminf(ay, by) - err_y, fy = fmaxf(ay, by) + err_y;
+        const float nz = fminf(az, bz) - err_z, fz = fmaxf(az, bz) + err_z;
+        const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
+        const float hi = fminf(fminf(fx, fy), fminf(fz, t_hi));
+        t_entry = lo;
+        return hi * 1.000002f + 1e-30f >= lo;
+    }
 };
 
 // x / y where x == 0 is frequent: a bounce ray leaving an axis-aligned wall has a numerator of exactly 0 against that
@@ -441,6 +466,178 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
         }
     }
     return best;
+}
+
+// Ordered form of the scan for large programs under WRT_CULL_TIGHT: near-child-first descent over the child-pair
+// records with a short per-thread stack, so the running tmax shrinks early and far subtrees are never opened (the fixed
+// DFS order visits ~3 500 nodes per ray on the 2^20-primitive scene, this visits a few hundred).
+// The visiting order differs from the reference's, the RESULT does not: among hits with the minimal t the reference's
+// sequential rule (sphere accepts t < tmax, quad accepts t <= tmax, in DFS order) keeps the first of them in DFS order
+// unless a later one is a quad, in which case the last such quad wins.  Ops are numbered in DFS order, so tracking
+// (first op, last quad op) of the minimal-t set reproduces that rule under any visiting order.
+#define WRT_STACK_DEPTH 48
+// Resumable form: the traversal state lives in a struct so a warp can stop stepping when too few of its lanes are still
+// traversing, hand the finished lanes new rays, and resume the others where they were (render_kernel_lane).
+struct Trav {
+    double best_t;
+    d3 o, d;  // ray in the current transform context
+    uint32_t first_pc, first_xf, lastq_pc, lastq_xf;
+    uint32_t xf, pc, end, node;
+    int sp;
+    float t_lo;
+    Culler<WRT_CULL_TIGHT> cull;
+};
+
+__device__ __forceinline__ void trav_init(const DeviceScene& S, Trav& T, d3 wo, d3 wd, double time, double tmin, double tmax) {
+    (void)time;
+    T.best_t = tmax;
+    T.o = wo; T.d = wd;
+    T.first_pc = WRT_NONE; T.first_xf = WRT_NONE; T.lastq_pc = WRT_NONE; T.lastq_xf = WRT_NONE;
+    T.xf = WRT_NONE;
+    T.cull.set_ray(wo, wd);
+    T.sp = 0;
+    T.t_lo = __double2float_rd(tmin);
+    T.pc = 0; T.end = S.n_ops - 1;  // current op range (excludes OP_END)
+    T.node = WRT_NONE;              // != NONE: descend from this child-pair record instead
+}
+
+// One step (one child-pair record, one op, or one pop).  Returns true when the traversal is complete.
+__device__ __forceinline__ bool trav_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
+                                          double tmin, double tmax) {
+    if (T.node != WRT_NONE) {
+        const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
+        const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+        const float t_hi = __double2float_ru(T.best_t);
+        float el, er;
+        const bool hl = T.cull.entry(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, T.t_lo, t_hi, el);
+        const uint32_t r_desc = __float_as_uint(b0.w);
+        const bool hr = (r_desc != WRT_NONE) && T.cull.entry(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.t_lo, t_hi, er);
+        uint32_t go_desc = WRT_NONE, go_end = 0;
+        if (hl && hr) {
+            const bool left_first = el <= er;
+            const uint32_t far_desc = left_first ? r_desc : __float_as_uint(a0.w);
+            const uint32_t far_end = left_first ? __float_as_uint(b1.w) : __float_as_uint(a1.w);
+            if (T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(far_desc, far_end, T.xf, __float_as_uint(left_first ? er : el));
+            go_desc = left_first ? __float_as_uint(a0.w) : r_desc;
+            go_end = left_first ? __float_as_uint(a1.w) : __float_as_uint(b1.w);
+        } else if (hl) {
+            go_desc = __float_as_uint(a0.w); go_end = __float_as_uint(a1.w);
+        } else if (hr) {
+            go_desc = r_desc; go_end = __float_as_uint(b1.w);
+        }
+        if (go_desc != WRT_NONE) {
+            if (go_desc & 0x80000000u) { T.node = go_desc & 0x7FFFFFFFu; }
+            else { T.node = WRT_NONE; T.pc = go_desc; T.end = go_end; }
+            return false;
+        }
+        T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: pop below
+    }
+    if (T.pc >= T.end) {  // range exhausted: pop
+        while (T.sp > 0) {
+            const uint4 e = stack[--T.sp];
+            if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
+            if (e.z != T.xf) { T.xf = e.z; ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
+            if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
+            else { T.node = WRT_NONE; T.pc = e.x; T.end = e.y; }
+            return false;
+        }
+        return true;
+    }
+    const uint32_t pc = T.pc;
+    const uint4 op = __ldg(S.ops + pc);
+    const d3 o = T.o, d = T.d;
+    if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
+        if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
+        T.node = op.y;
+    } else if (op.x == OP_NODE_TIGHT_ONLY) {
+        T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
+    } else if (op.x == OP_SPHERE) {
+        const double2* g = reinterpret_cast<const double2*>(S.spheres + op.y);
+        double2 g0 = __ldg(g), g1 = __ldg(g + 1);
+        d3 center = mk(g0.x, g0.y, g1.x);
+        const double radius = g1.y;
+        if (S.has_moving) {
+            const SphereAux ax = S.sphere_aux[op.y];
+            if (ax.is_moving) center = center + mk(ax.mx, ax.my, ax.mz) * time;
+        }
+        d3 oc = center - o;
+        double a = dot(d, d);
+        double h = dot(d, oc);
+        double c = dot(oc, oc) - radius * radius;
+        double disc = h * h - a * c;
+        if (!(disc < 0.0)) {
+            double sq = sqrt(disc);
+            double root = (h - sq) / a;
+            if (!(tmin < root)) root = (h + sq) / a;  // the near root is unusable: the reference then tries the far one
+            if ((tmin < root) && (root <= T.best_t) && (root < tmax)) {
+                if (root < T.best_t) { T.best_t = root; T.first_pc = pc; T.first_xf = T.xf; T.lastq_pc = WRT_NONE; }
+                else if (pc < T.first_pc) { T.first_pc = pc; T.first_xf = T.xf; }
+            }
+        }
+        T.pc = pc + 1;
+    } else if (op.x == OP_QUAD) {
+        const double2* g = reinterpret_cast<const double2*>(S.quads + op.y);
+        double2 n0 = __ldg(g), n1 = __ldg(g + 1);
+        d3 n = mk(n0.x, n0.y, n1.x);
+        double denom = dot(n, d);
+        if (!(fabs(denom) < 1e-8)) {
+            double t = div_zero_aware(n1.y - dot(n, o), denom);
+            if ((tmin <= t) && (t <= T.best_t)) {
+                double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
+                double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                d3 p = o + d * t;
+                d3 planar = p - mk(s0.x, s0.y, s1.x);
+                d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
+                double alpha = dot(bw, cross(planar, bv));
+                double beta = dot(bw, cross(bu, planar));
+                if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
+                    if (t < T.best_t) { T.best_t = t; T.first_pc = pc; T.first_xf = T.xf; T.lastq_pc = pc; T.lastq_xf = T.xf; }
+                    else {
+                        if (pc < T.first_pc) { T.first_pc = pc; T.first_xf = T.xf; }
+                        if (T.lastq_pc == WRT_NONE || pc > T.lastq_pc) { T.lastq_pc = pc; T.lastq_xf = T.xf; }
+                    }
+                }
+            }
+        }
+        T.pc = pc + 1;
+    } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
+        apply_xform(S.xforms[op.y], T.o, T.d);
+        T.xf = op.y;
+        T.cull.set_ray(T.o, T.d);
+        T.pc = pc + 1;
+    } else if (op.x == OP_POP) {
+        T.xf = op.y;
+        ray_in_xform(S, T.xf, wo, wd, T.o, T.d);
+        T.cull.set_ray(T.o, T.d);
+        T.pc = pc + 1;
+    } else {
+        T.pc = T.end;  // OP_END
+    }
+    return false;
+}
+
+__device__ __forceinline__ ClosestHit trav_result(const Trav& T) {
+    ClosestHit best;
+    best.t = T.best_t;
+    const bool quad_wins = (T.lastq_pc != WRT_NONE) && (T.first_pc != WRT_NONE) && (T.lastq_pc > T.first_pc);
+    best.pc = quad_wins ? T.lastq_pc : T.first_pc;
+    best.xform = quad_wins ? T.lastq_xf : T.first_xf;
+    return best;
+}
+
+__device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
+    Trav T;
+    uint4 stack[WRT_STACK_DEPTH];  // {desc | first op, end op, xform, entry distance bits}
+    trav_init(S, T, wo, wd, time, tmin, tmax);
+    while (!trav_step(S, T, stack, wo, wd, time, tmin, tmax)) {}
+    return trav_result(T);
+}
+
+// per-lane scan: ordered descent where it applies (tight culling, stack deep enough for the tree), else the DFS-order scan
+template <int CULL>
+__device__ __forceinline__ ClosestHit closest_hit_lane(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
+    if (CULL == WRT_CULL_TIGHT && S.use_ordered) return closest_hit_ordered(S, wo, wd, time, tmin, tmax);
+    return closest_hit<CULL>(S, wo, wd, time, tmin, tmax);
 }
 
 // Packet form of the same scan for small programs (a few dozen ops: Cornell box, emissive, ...): the program counter

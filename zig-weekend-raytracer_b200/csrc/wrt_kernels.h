@@ -13,6 +13,8 @@
 #define WRT_SYNC_BLOCK 512  // phase-synchronous variant: one block of 16 warps per SM
 // Programs up to this many ops are scanned with the warp-uniform packet traversal.
 #define WRT_PACKET_MAX_OPS 96u
+// Programs larger than this use the resumable per-lane kernel (terminated-ray replacement inside the traversal loop).
+#define WRT_LANE_KERNEL_MIN_OPS 65536u
 
 namespace wrt {
 
@@ -66,7 +68,7 @@ cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet,
                           cudaStream_t stream);
 cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
                                unsigned long long* counters, cudaStream_t stream);
-cudaError_t render_occupancy(uint32_t cull_mode, bool packet, int* blocks_per_sm);
+cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm);
 cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
                            uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream);
 cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* rgb8, cudaStream_t stream);

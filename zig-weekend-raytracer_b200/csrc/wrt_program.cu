@@ -166,12 +166,20 @@ struct Compiler {
         r.max_x = e.bbox_max[0]; r.max_y = e.bbox_max[1];
         out.boxes_ref.push_back(r);
         out.boxes_tight.push_back(padded(tb));
+        Node2 none;
+        std::memset(&none, 0, sizeof none);
+        none.l_desc = none.r_desc = WRT_NONE;
+        out.nodes2.push_back(none);  // filled in for bvh_node ops, stays empty for instance bounds
         return (uint32_t)(out.boxes_ref.size() - 1);
     }
 
     // ---- program emission ------------------------------------------------------------------------------
+    uint32_t nest = 0;  // current nesting of bvh_node / instance ops (bounds the ordered traversal's stack)
     bool emit(uint32_t id, uint32_t xf, uint32_t xf_depth) {
         if (!check_entity(id, "emit")) return false;
+        struct Nest { uint32_t& n; uint32_t& mx; bool on; Nest(uint32_t& n_, uint32_t& mx_, bool on_) : n(n_), mx(mx_), on(on_) { if (on) { ++n; if (n > mx) mx = n; } } ~Nest() { if (on) --n; } };
+        const uint32_t kind_for_nest = sc->entities[id].kind;
+        Nest nest_guard(nest, out.max_nesting, kind_for_nest == WRT_ENT_BVH_NODE || kind_for_nest == WRT_ENT_TRANSLATE || kind_for_nest == WRT_ENT_ROTATE_Y);
         if (on_stack[id]) return fail(WRT_E_INVALID, "entity graph contains a cycle");
         on_stack[id] = 1;
         const wrt_entity& e = sc->entities[id];
@@ -199,10 +207,31 @@ struct Compiler {
                 const uint32_t box = push_box(e, tb);
                 const size_t at = out.ops.size();
                 out.ops.push_back(make_uint4(OP_NODE, box, 0, 0));
+                const uint32_t l_start = (uint32_t)out.ops.size();
                 ok = emit(e.a, xf, xf_depth);
+                const uint32_t r_start = (uint32_t)out.ops.size();
                 // span == 1 nodes hold the same child twice (entity.zig:231-233); the second visit cannot change the result
                 if (ok && e.b != e.a) ok = emit(e.b, xf, xf_depth);
-                out.ops[at].z = (uint32_t)out.ops.size();
+                const uint32_t end = (uint32_t)out.ops.size();
+                out.ops[at].z = end;
+                if (ok) {  // child-pair record for the ordered traversal: both children's boxes + where they live in the program
+                    Node2 n2;
+                    Box3 lb, rb;
+                    lb.reset(); rb.reset();
+                    if (!tight_box(e.a, lb)) { ok = false; break; }
+                    if (e.b != e.a && !tight_box(e.b, rb)) { ok = false; break; }
+                    const BoxTight pl = padded(lb), pr = padded(rb);
+                    auto desc = [&](uint32_t start) {
+                        return out.ops[start].x == OP_NODE ? (0x80000000u | out.ops[start].y) : start;
+                    };
+                    n2.lmin[0] = pl.min_x; n2.lmin[1] = pl.min_y; n2.lmin[2] = pl.min_z; n2.l_desc = desc(l_start);
+                    n2.lmax[0] = pl.max_x; n2.lmax[1] = pl.max_y; n2.lmax[2] = pl.max_z; n2.l_end = r_start;
+                    n2.rmin[0] = pr.min_x; n2.rmin[1] = pr.min_y; n2.rmin[2] = pr.min_z;
+                    n2.rmax[0] = pr.max_x; n2.rmax[1] = pr.max_y; n2.rmax[2] = pr.max_z;
+                    n2.r_desc = (r_start < end) ? desc(r_start) : WRT_NONE;
+                    n2.r_end = end;
+                    out.nodes2[box] = n2;
+                }
                 break;
             }
             case WRT_ENT_TRANSLATE:
@@ -374,6 +403,10 @@ struct Compiler {
             out.boxes_ref.push_back(r);
             Box3 e; e.reset();
             out.boxes_tight.push_back(padded(e));
+            Node2 none;
+            std::memset(&none, 0, sizeof none);
+            none.l_desc = none.r_desc = WRT_NONE;
+            out.nodes2.push_back(none);
         }
         return code;
     }

@@ -13,6 +13,7 @@ struct CompiledScene {
     std::vector<uint4> ops;
     std::vector<BoxRef> boxes_ref;
     std::vector<BoxTight> boxes_tight;
+    std::vector<Node2> nodes2;  // parallel to boxes_*: child-pair records of the bvh_node ops (ordered traversal)
     std::vector<SphereGeom> spheres;
     std::vector<SphereAux> sphere_aux;  // empty unless a sphere moves
     std::vector<QuadGeom> quads;
@@ -23,6 +24,7 @@ struct CompiledScene {
     std::vector<Light> lights;
     uint32_t n_prims = 0;
     uint32_t max_xform_depth = 0;
+    uint32_t max_nesting = 0;  // deepest chain of bvh_node / instance ops
     bool has_lights = false;
     bool has_moving = false;
 };
