@@ -197,6 +197,7 @@ typedef struct wrt_params {
 #define WRT_FLAG_ENGINE_MEGAKERNEL 16u /* force the persistent megakernel (default: chosen by the amount of work) */
 #define WRT_FLAG_ENGINE_WAVEFRONT 32u  /* force the wavefront engine (path pool + per-material queues in HBM) */
 #define WRT_FLAG_ENGINE_SYNC 64u       /* phase-synchronous megakernel: one 16-warp block per SM, block barriers between phases */
+#define WRT_FLAG_ENGINE_REGROUP 128u   /* phase-synchronous megakernel + per-material regrouping of the block's paths in shared memory */
 /* the same two switches for wrt_trace_rays, OR-ed into its cull_mode argument */
 #define WRT_TRAV_FORCE_LANE 0x100u
 #define WRT_TRAV_FORCE_PACKET 0x200u

@@ -18,6 +18,7 @@ WRT_FLAG_FORCE_PACKET = 8
 WRT_FLAG_ENGINE_MEGAKERNEL = 16
 WRT_FLAG_ENGINE_WAVEFRONT = 32
 WRT_FLAG_ENGINE_SYNC = 64
+WRT_FLAG_ENGINE_REGROUP = 128
 WRT_TRAV_FORCE_LANE = 0x100
 WRT_TRAV_FORCE_PACKET = 0x200
 

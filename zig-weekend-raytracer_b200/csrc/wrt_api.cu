@@ -423,8 +423,12 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     CU(wrt::render_occupancy(ctx->ds, p.cull_mode, packet, &blocks_per_sm));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const bool sync_engine = (p.flags & WRT_FLAG_ENGINE_SYNC) != 0;
-    const uint32_t grid = sync_engine ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
-    const uint64_t resident_warps = sync_engine ? (uint64_t)grid * (WRT_SYNC_BLOCK / 32) : (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
+    // regrouping kernel: packet programs without moving spheres (its staging area carries no ray time)
+    const bool regroup_engine = !sync_engine && (p.flags & WRT_FLAG_ENGINE_REGROUP) && packet && !ctx->cs.has_moving;
+    const bool block_per_sm = sync_engine || regroup_engine;
+    const uint32_t grid = block_per_sm ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
+    const uint64_t resident_warps = regroup_engine ? (uint64_t)grid * (WRT_REGROUP_BLOCK / 32)
+                                    : sync_engine ? (uint64_t)grid * (WRT_SYNC_BLOCK / 32) : (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
     // Engine: the persistent megakernel is the default — on the measured configs it matches the
     // wavefront (queues in HBM, one small kernel per stage) without its state traffic; the wavefront is selected by flag.
@@ -499,7 +503,8 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         wf_rays = ctx->h_wf_counters[8];
         wf_paths = ctx->h_wf_counters[9];
     } else if (rc.total_jobs > 0) {
-        if (sync_engine) CU(wrt::launch_render_sync(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        if (regroup_engine) CU(wrt::launch_render_regroup(ctx->ds, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        else if (sync_engine) CU(wrt::launch_render_sync(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         else CU(wrt::launch_render(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         ++launches;
     }

@@ -8,8 +8,12 @@
 
 #define WRT_RENDER_BLOCK 128
 #ifndef WRT_RENDER_MIN_BLOCKS
-#define WRT_RENDER_MIN_BLOCKS 4  // <= 128 registers per thread: 16 warps per SM
+#define WRT_RENDER_MIN_BLOCKS 4  // per-lane kernels (traversal stack): <= 128 registers per thread, 16 warps per SM
 #endif
+#ifndef WRT_PACKET_MIN_BLOCKS
+#define WRT_PACKET_MIN_BLOCKS 6  // packet kernel: <= 85 registers, 24 warps per SM (measured best of 3/4/5/6/8 on C2)
+#endif
+#define WRT_REGROUP_BLOCK 768  // regrouping variant: one block of 24 warps per SM (<= 85 registers)
 #define WRT_SYNC_BLOCK 512  // phase-synchronous variant: one block of 16 warps per SM
 // Programs up to this many ops are scanned with the warp-uniform packet traversal.
 #define WRT_PACKET_MAX_OPS 96u
@@ -66,6 +70,8 @@ cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stre
 
 cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream);
+cudaError_t launch_render_regroup(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+                                  cudaStream_t stream);
 cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
                                unsigned long long* counters, cudaStream_t stream);
 cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm);
