@@ -372,6 +372,12 @@ def test_wavefront_engine_is_bit_identical_to_megakernel(ctx, wrt, wro, images, 
         np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64))
         assert (sa.rays, sa.paths) == (sb.rays, sb.paths)
         assert sb.kernel_launches > sa.kernel_launches
+        # the phase-synchronous and the shared-memory regrouping schedules of the megakernel
+        for flag in (wrt.WRT_FLAG_ENGINE_SYNC, wrt.WRT_FLAG_ENGINE_REGROUP):
+            c = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=flag))
+            sc_ = ctx.stats()
+            np.testing.assert_array_equal(a.view(np.uint64), c.view(np.uint64))
+            assert (sa.rays, sa.paths) == (sc_.rays, sc_.paths)
     sc.close()
 
 
