@@ -198,6 +198,11 @@ typedef struct wrt_params {
 #define WRT_FLAG_ENGINE_WAVEFRONT 32u  /* force the wavefront engine (path pool + per-material queues in HBM) */
 #define WRT_FLAG_ENGINE_SYNC 64u       /* phase-synchronous megakernel: one 16-warp block per SM, block barriers between phases */
 #define WRT_FLAG_ENGINE_REGROUP 128u   /* phase-synchronous megakernel + per-material regrouping of the block's paths in shared memory */
+/* Sample chunks: a pixel's samples are summed in order inside a chunk and the chunk sums are added in order, so the
+ * chunk count fixes the last bits of the frame.  By default it is chosen from the full frame size, the sample count and
+ * the engine (never from the shard or the GPU), so a frame is bit-identical on 1..8 GPUs; WRT_FLAG_CHUNKS(n), n in
+ * 1..255, pins it — two engines given the same n produce the same bits. */
+#define WRT_FLAG_CHUNKS(n) (((uint32_t)(n) & 0xFFu) << 24)
 /* the same two switches for wrt_trace_rays, OR-ed into its cull_mode argument */
 #define WRT_TRAV_FORCE_LANE 0x100u
 #define WRT_TRAV_FORCE_PACKET 0x200u

@@ -359,22 +359,24 @@ def test_full_size_cornell_config_properties(ctx, wrt, wro):
 @pytest.mark.parametrize("name", ["cornell_box", "emissive", "balls", "rtw_final", "earth", "shrek_quads"])
 def test_wavefront_engine_is_bit_identical_to_megakernel(ctx, wrt, wro, images, name):
     """Same integrator, two schedules (persistent megakernel vs. path pool + per-material queues): every slot adds its
-    samples in sample order in both, so the frames, ray counts and path counts are identical."""
+    samples in sample order in both, so with the chunk count pinned (WRT_FLAG_CHUNKS) the frames, ray counts and path
+    counts are identical."""
     sc = wro.OracleScene(name, seed=1, images=images)
     ctx.upload_scene(sc.flatten())
     w, h = 61, 37
     cam = sc.camera(w, h)
+    chunks = wrt.WRT_FLAG_CHUNKS(3)
     for cull in (wrt.WRT_CULL_TIGHT, wrt.WRT_CULL_REFERENCE):
-        a = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_MEGAKERNEL))
+        a = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_MEGAKERNEL | chunks))
         sa = ctx.stats()
-        b = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_WAVEFRONT))
+        b = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=wrt.WRT_FLAG_ENGINE_WAVEFRONT | chunks))
         sb = ctx.stats()
         np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64))
         assert (sa.rays, sa.paths) == (sb.rays, sb.paths)
         assert sb.kernel_launches > sa.kernel_launches
         # the phase-synchronous and the shared-memory regrouping schedules of the megakernel
         for flag in (wrt.WRT_FLAG_ENGINE_SYNC, wrt.WRT_FLAG_ENGINE_REGROUP):
-            c = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=flag))
+            c = ctx.render(cam, sc.params(w, h, 6, 20, seed=5, cull_mode=cull, flags=flag | chunks))
             sc_ = ctx.stats()
             np.testing.assert_array_equal(a.view(np.uint64), c.view(np.uint64))
             assert (sa.rays, sa.paths) == (sc_.rays, sc_.paths)

@@ -19,6 +19,13 @@ WRT_FLAG_ENGINE_MEGAKERNEL = 16
 WRT_FLAG_ENGINE_WAVEFRONT = 32
 WRT_FLAG_ENGINE_SYNC = 64
 WRT_FLAG_ENGINE_REGROUP = 128
+
+
+def WRT_FLAG_CHUNKS(n: int) -> int:
+    """Pin the number of sample chunks (include/wrt.h): two engines given the same n produce the same bits."""
+    return (int(n) & 0xFF) << 24
+
+
 WRT_TRAV_FORCE_LANE = 0x100
 WRT_TRAV_FORCE_PACKET = 0x200
 

@@ -85,7 +85,9 @@ struct wrt_ctx {
     bool have_scene = false;
     wrt::CompiledScene cs;
     wrt::DeviceScene ds{};
+    wrt::DeviceScene ds_pruned{};  // ds with the pruned program (packet scan, WRT_CULL_TIGHT); == ds when nothing was dropped
     DevBuf<uint4> d_ops;
+    DevBuf<uint4> d_ops_pruned;
     DevBuf<wrt::BoxRef> d_boxes_ref;
     DevBuf<wrt::BoxTight> d_boxes_tight;
     DevBuf<wrt::Node2> d_nodes2;
@@ -195,7 +197,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->free_images();
-    ctx->d_ops.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
+    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
@@ -276,6 +278,7 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     if (rc != WRT_OK) return rc;
     wrt::CompiledScene& cs = ctx->cs;
     CU(ctx->d_ops.upload(cs.ops, ctx->stream));
+    if (!cs.ops_pruned.empty()) CU(ctx->d_ops_pruned.upload(cs.ops_pruned, ctx->stream));
     CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
     CU(ctx->d_boxes_tight.upload(cs.boxes_tight, ctx->stream));
     CU(ctx->d_nodes2.upload(cs.nodes2, ctx->stream));
@@ -298,6 +301,8 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     ds.has_lights = cs.has_lights ? 1u : 0u;
     ds.has_moving = cs.has_moving ? 1u : 0u;
     ds.use_ordered = (cs.max_nesting + 8 <= WRT_STACK_DEPTH) ? 1u : 0u;
+    ctx->ds_pruned = ds;
+    if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
     ctx->have_scene = true;
     ctx->stats.program_ops = ds.n_ops;
     ctx->stats.n_prims = cs.n_prims;
@@ -362,6 +367,12 @@ static bool use_packet(const wrt_ctx* ctx, uint32_t flags) {
     return ctx->cs.ops.size() <= WRT_PACKET_MAX_OPS;
 }
 
+// The scene view a launch scans: the packet traversal under WRT_CULL_TIGHT reads the pruned program (wrt_program.cu,
+// prune_program); everything else — reference culling, per-lane and ordered traversal (Node2 records index `ops`) — the full one.
+static const wrt::DeviceScene& scene_view(const wrt_ctx* ctx, uint32_t cull_mode, bool packet) {
+    return (packet && cull_mode == WRT_CULL_TIGHT) ? ctx->ds_pruned : ctx->ds;
+}
+
 static uint32_t shard_rows(const wrt_params& p) {
     if (p.row_shard_index >= p.height) return 0;
     return (p.height - p.row_shard_index + p.row_shard_count - 1) / p.row_shard_count;
@@ -416,44 +427,54 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     const uint32_t n_pixels = (uint32_t)n_pixels64;
     const uint32_t n_samples = p.sample_end - p.sample_begin;
 
-    // Job decomposition: (row x 32-column block) as in the reference (render.zig:55-73), times a sample split
-    // chosen so that the persistent grid has >= 16 jobs per resident warp to balance uneven path lengths.
+    // Job decomposition: the reference's (row x column block) jobs (render.zig:55-73) times a sample split; render_kernel
+    // hands the same work out per lane (pixel x sample chunk).
     int blocks_per_sm = 0;
     const bool packet = use_packet(ctx, p.flags);
-    CU(wrt::render_occupancy(ctx->ds, p.cull_mode, packet, &blocks_per_sm));
+    const wrt::DeviceScene& view = scene_view(ctx, p.cull_mode, packet);
+    CU(wrt::render_occupancy(view, p.cull_mode, packet, &blocks_per_sm));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const bool sync_engine = (p.flags & WRT_FLAG_ENGINE_SYNC) != 0;
     // regrouping kernel: packet programs without moving spheres (its staging area carries no ray time)
     const bool regroup_engine = !sync_engine && (p.flags & WRT_FLAG_ENGINE_REGROUP) && packet && !ctx->cs.has_moving;
     const bool block_per_sm = sync_engine || regroup_engine;
     const uint32_t grid = block_per_sm ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
-    const uint64_t resident_warps = regroup_engine ? (uint64_t)grid * (WRT_REGROUP_BLOCK / 32)
-                                    : sync_engine ? (uint64_t)grid * (WRT_SYNC_BLOCK / 32) : (uint64_t)grid * (WRT_RENDER_BLOCK / 32);
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
     // Engine: the persistent megakernel is the default — on the measured configs it matches the
     // wavefront (queues in HBM, one small kernel per stage) without its state traffic; the wavefront is selected by flag.
     bool wavefront = false;
     if (p.flags & WRT_FLAG_ENGINE_MEGAKERNEL) wavefront = false;
     if ((p.flags & WRT_FLAG_ENGINE_WAVEFRONT) && p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0) wavefront = true;
+    // Sample chunks (include/wrt.h, WRT_FLAG_CHUNKS): a function of the FULL frame, the sample count and the engine only —
+    // not of the shard or the grid — so the per-pixel summation tree, and with it every bit of the frame, is the same on
+    // 1 or 8 GPUs.  The accumulators (chunks x shard pixels x 24 B) stay under 0.8 GB for frames of up to 2^25 pixels.
     uint32_t n_chunks = 1;
-    if (wavefront) {
-        // pool of ~4M path slots: slot = (sample chunk, pixel)
-        uint64_t want = ((4ull << 20) + n_pixels64 - 1) / n_pixels64;
-        if (want < 1) want = 1;
-        if (want > 64) want = 64;
-        if (want > n_samples) want = n_samples;
-        n_chunks = (uint32_t)want;
-    } else if (base_jobs > 0 && n_samples > 0) {
-        uint64_t want = (16 * resident_warps + base_jobs - 1) / base_jobs;
-        if (want < 1) want = 1;
-        if (want > 64) want = 64;
-        if (want > n_samples) want = n_samples;
-        n_chunks = (uint32_t)want;
+    const uint64_t frame_pixels = (uint64_t)p.width * p.height;
+    const uint32_t forced_chunks = p.flags >> 24;
+    if (n_samples > 0) {
+        uint64_t want, min_chunk;
+        if (wavefront) {
+            want = ((4ull << 20) + frame_pixels - 1) / frame_pixels;  // pool of ~4M path slots: slot = (sample chunk, pixel)
+            min_chunk = 1;
+        } else {
+            // 2^25 (pixel, chunk) jobs per frame: a few dozen per resident lane even when 8 GPUs share the frame.  The packet
+            // kernel takes jobs per lane and is happy with chunks of 4 samples; the kernels that take jobs per warp wait for
+            // the longest lane of each job, which only averages out over chunks of a few hundred samples.
+            want = ((1ull << 25) + frame_pixels - 1) / frame_pixels;
+            const bool lane_jobs = packet && !sync_engine && !regroup_engine;
+            min_chunk = lane_jobs ? 4 : 256;
+        }
+        want = std::min<uint64_t>(want, 64);
+        want = std::min<uint64_t>(want, (n_samples + min_chunk - 1) / min_chunk);
+        if (forced_chunks) want = std::min<uint64_t>(forced_chunks, n_samples);
+        n_chunks = (uint32_t)std::max<uint64_t>(want, 1);
     }
     rc.chunk_size = n_samples ? (n_samples + n_chunks - 1) / n_chunks : 1;
     if (rc.chunk_size == 0) rc.chunk_size = 1;
     rc.n_chunks = n_samples ? (n_samples + rc.chunk_size - 1) / rc.chunk_size : 0;
     rc.total_jobs = (unsigned long long)rc.n_chunks * base_jobs;
+    rc.n_pixels_local = n_pixels;
+    rc.lane_jobs = (unsigned long long)rc.n_chunks * n_pixels64;
 
     CU(ctx->d_accum.ensure((size_t)std::max<uint32_t>(rc.n_chunks, 1) * n_pixels64 * 3));
     CU(ctx->d_rgb8.ensure((size_t)n_pixels64 * 3));
@@ -491,7 +512,7 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         const uint32_t check_every = 16;
         bool done = false;
         for (uint64_t it = 0; it < max_iters && !done; ++it) {
-            CU(wrt::wf_launch_iteration(A, ctx->ds, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
+            CU(wrt::wf_launch_iteration(A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
             launches += 6;
             if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
                 CU(cudaMemcpyAsync(ctx->h_wf_counters, A.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -503,9 +524,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         wf_rays = ctx->h_wf_counters[8];
         wf_paths = ctx->h_wf_counters[9];
     } else if (rc.total_jobs > 0) {
-        if (regroup_engine) CU(wrt::launch_render_regroup(ctx->ds, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
-        else if (sync_engine) CU(wrt::launch_render_sync(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
-        else CU(wrt::launch_render(ctx->ds, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        if (regroup_engine) CU(wrt::launch_render_regroup(view, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        else if (sync_engine) CU(wrt::launch_render_sync(view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        else CU(wrt::launch_render(view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -624,7 +645,7 @@ extern "C" int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double*
         TRY(cudaMemcpyAsync(d_o.p, origins, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         TRY(cudaMemcpyAsync(d_d.p, directions, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         uint32_t grid = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * 32);
-        TRY(wrt::launch_trace_rays(ctx->ds, cull_mode, packet, d_o.p, d_d.p, n, tmin, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr,
+        TRY(wrt::launch_trace_rays(scene_view(ctx, cull_mode, packet), cull_mode, packet, d_o.p, d_d.p, n, tmin, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr,
                                    point ? d_p.p : nullptr, normal ? d_n.p : nullptr, uv ? d_uv.p : nullptr,
                                    front_face ? d_ff.p : nullptr, grid, ctx->stream));
         if (prim_ids) TRY(cudaMemcpyAsync(prim_ids, d_ids.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

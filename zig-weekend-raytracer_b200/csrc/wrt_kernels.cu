@@ -243,54 +243,67 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
     const bool need_time = S.has_moving != 0;
     Rng rng;
     rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
+    rng.pixel = 0; rng.sample = 0;
 
-    for (;;) {
-        unsigned long long job = 0;
-        if (lane == 0) job = atomicAdd(&counters[0], 1ull);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= rc.total_jobs) break;
-        // job -> (chunk, local row, column block); chunks outermost
-        const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
-        const uint32_t chunk = (uint32_t)(job / blocks_per_chunk);
-        const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
-        const uint32_t local_row = rem / rc.n_col_blocks;
-        const uint32_t col = (rem % rc.n_col_blocks) * 32u + lane;
-        const uint32_t row = rc.row_shard_index + local_row * rc.row_shard_count;
-        const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
-        const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
-        const bool lane_active = col < rc.width;
-
+    if (TRAV == TRAV_PACKET) {
+        // Packet scan: work is handed out per LANE.  A lane job is (pixel of the shard, sample chunk), and a lane that finishes its job takes
+        // the next one while its neighbours are still mid-chunk, so no lane waits for the longest path sum of its warp and
+        // the kernel's tail is one lane job.  The warp draws its lanes' jobs with one atomic (ballot + prefix count).
+        unsigned long long job = 0;     // this lane's job
+        bool have_job = false, drained = false;
+        uint32_t col = 0, row = 0, s = 0, s_last = 0;
         d3 color = mk(0, 0, 0);
-        uint32_t s = s_first;
         bool alive = false;
         uint32_t depth_left = 0;
         Ray ray;
         ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
         d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
-        rng.pixel = row * rc.width + col;
-        rng.sample = 0;
 
         for (;;) {
-            if (!alive && lane_active && s < s_last) {
+            const bool want = !have_job && !drained;
+            const uint32_t wanting = __ballot_sync(0xffffffffu, want);
+            if (wanting) {
+                const int leader = __ffs(wanting) - 1;
+                unsigned long long first = 0;
+                if ((int)lane == leader) first = atomicAdd(&counters[0], (unsigned long long)__popc(wanting));
+                first = __shfl_sync(0xffffffffu, first, leader);
+                if (want) {
+                    job = first + __popc(wanting & ((1u << lane) - 1u));
+                    if (job < rc.lane_jobs) {  // job -> (chunk, pixel of the shard); chunks outermost
+                        const uint32_t chunk = (uint32_t)(job / rc.n_pixels_local);
+                        const uint32_t pix = (uint32_t)(job % rc.n_pixels_local);
+                        const uint32_t local_row = pix / rc.width;
+                        col = pix - local_row * rc.width;
+                        row = rc.row_shard_index + local_row * rc.row_shard_count;
+                        s = rc.sample_begin + chunk * rc.chunk_size;
+                        s_last = min(s + rc.chunk_size, rc.sample_end);
+                        color = mk(0, 0, 0);
+                        rng.pixel = row * rc.width + col;
+                        have_job = true;
+                        if (rc.max_depth == 0) {  // depth 0 returns black for every sample (render.zig:199)
+                            double* slot = accum + job * 3ull;
+                            slot[0] = 0.0; slot[1] = 0.0; slot[2] = 0.0;
+                            n_paths += s_last - s;
+                            have_job = false;
+                        }
+                    } else {
+                        drained = true;
+                    }
+                }
+            }
+            if (!alive && have_job) {
                 rng.sample = s;
                 ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
                 beta = mk(1, 1, 1); L = mk(0, 0, 0);
                 depth_left = rc.max_depth;
-                alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
+                alive = true;
                 ++n_paths;
-                if (!alive) ++s;
             }
             if (!__any_sync(0xffffffffu, alive)) {
-                if (!__any_sync(0xffffffffu, lane_active && s < s_last)) break;
+                if (__all_sync(0xffffffffu, drained)) break;  // no lane has a job left and the queue is empty
                 continue;
             }
-            ClosestHit ch;
-            if (TRAV == TRAV_PACKET) {
-                ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
-            } else {
-                ch.pc = WRT_NONE;
-                if (alive) ch = closest_hit_lane<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
-            }
+            const ClosestHit ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
             if (alive) {
                 ++n_rays;
                 const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
@@ -299,13 +312,76 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                     if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
                     color = color + L * scale;     // render.zig:129-135
                     alive = false;
-                    ++s;
+                    if (++s == s_last) {           // chunk complete: its sum goes to the (chunk, pixel) slot == job index
+                        double* slot = accum + job * 3ull;
+                        slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
+                        have_job = false;
+                    }
                 }
             }
         }
-        if (lane_active) {
-            double* slot = accum + ((size_t)chunk * rc.n_rows_local * rc.width + (size_t)local_row * rc.width + col) * 3;
-            slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
+    } else {
+        // Per-lane scan: warp jobs (row, 32-column block, sample chunk) keep the lanes of a warp on neighbouring pixels, whose
+        // traversals are of similar length; lanes still regenerate their own samples inside the job.
+        for (;;) {
+            unsigned long long job = 0;
+            if (lane == 0) job = atomicAdd(&counters[0], 1ull);
+            job = __shfl_sync(0xffffffffu, job, 0);
+            if (job >= rc.total_jobs) break;
+            // job -> (chunk, local row, column block); chunks outermost
+            const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
+            const uint32_t chunk = (uint32_t)(job / blocks_per_chunk);
+            const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
+            const uint32_t local_row = rem / rc.n_col_blocks;
+            const uint32_t col = (rem % rc.n_col_blocks) * 32u + lane;
+            const uint32_t row = rc.row_shard_index + local_row * rc.row_shard_count;
+            const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
+            const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
+            const bool lane_active = col < rc.width;
+
+            d3 color = mk(0, 0, 0);
+            uint32_t s = s_first;
+            bool alive = false;
+            uint32_t depth_left = 0;
+            Ray ray;
+            ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
+            d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
+            rng.pixel = row * rc.width + col;
+            rng.sample = 0;
+
+            for (;;) {
+                if (!alive && lane_active && s < s_last) {
+                    rng.sample = s;
+                    ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
+                    beta = mk(1, 1, 1); L = mk(0, 0, 0);
+                    depth_left = rc.max_depth;
+                    alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
+                    ++n_paths;
+                    if (!alive) ++s;
+                }
+                if (!__any_sync(0xffffffffu, alive)) {
+                    if (!__any_sync(0xffffffffu, lane_active && s < s_last)) break;
+                    continue;
+                }
+                ClosestHit ch;
+                ch.pc = WRT_NONE;
+                if (alive) ch = closest_hit_lane<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+                if (alive) {
+                    ++n_rays;
+                    const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
+                    --depth_left;
+                    if (!cont || depth_left == 0) {
+                        if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
+                        color = color + L * scale;     // render.zig:129-135
+                        alive = false;
+                        ++s;
+                    }
+                }
+            }
+            if (lane_active) {
+                double* slot = accum + ((size_t)chunk * rc.n_rows_local * rc.width + (size_t)local_row * rc.width + col) * 3;
+                slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
+            }
         }
     }
     // ray / path accounting: one atomic per warp

@@ -31,10 +31,12 @@ struct RenderConstants {
     wrt_camera cam;
     double background[3];
     unsigned long long seed;
-    unsigned long long total_jobs;  // n_chunks * n_rows_local * n_col_blocks
+    unsigned long long total_jobs;  // warp jobs: n_chunks * n_rows_local * n_col_blocks (lane / sync / regroup kernels)
+    unsigned long long lane_jobs;   // lane jobs: n_chunks * n_pixels_local (render_kernel)
     uint32_t width, height, spp, max_depth, dof;
     uint32_t row_shard_index, row_shard_count, n_rows_local, n_col_blocks;
     uint32_t sample_begin, sample_end, chunk_size, n_chunks;
+    uint32_t n_pixels_local, _pad0;
 };
 
 // ---- wavefront engine (wrt_kernels.cu) ----

@@ -373,6 +373,58 @@ struct Compiler {
         return true;
     }
 
+    // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` minus the nodes whose conservative box
+    // cannot cull anything their nearest kept ancestor has not culled already — surface area >= 90 % of that ancestor's,
+    // compared within one coordinate frame (a translation keeps the extents, a rotation starts afresh).  The Cornell box
+    // is the type case: its BVH puts one wall in each half, so 7 of its 8 bvh_node boxes are the whole room and every ray
+    // passes them.  Tight boxes are conservative, so dropping a test never changes a result; skip links are re-indexed.
+    // WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
+    void prune_program() {
+        const size_t n = out.ops.size();
+        struct Enclosing { uint32_t end; double area; };
+        std::vector<Enclosing> stack;      // kept nodes around the current op, innermost last
+        std::vector<size_t> frame_base;    // stack height at each open PUSH (ancestors below it live in another frame)
+        std::vector<uint8_t> keep(n, 1);
+        auto area_of = [&](uint32_t box) {
+            const BoxTight& b = out.boxes_tight[box];
+            const double dx = (double)b.max_x - b.min_x, dy = (double)b.max_y - b.min_y, dz = (double)b.max_z - b.min_z;
+            if (!(dx >= 0.0 && dy >= 0.0 && dz >= 0.0)) return -1.0;  // empty / inverted: keep the test, it culls everything
+            return 2.0 * (dx * dy + dy * dz + dz * dx);
+        };
+        for (size_t pc = 0; pc < n; ++pc) {
+            const uint4 op = out.ops[pc];
+            const size_t base = frame_base.empty() ? 0 : frame_base.back();
+            while (stack.size() > base && stack.back().end <= pc) stack.pop_back();
+            if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) {
+                const double a = area_of(op.y);
+                if (stack.size() > base && a >= 0.0 && stack.back().area > 0.0 && a >= 0.9 * stack.back().area) keep[pc] = 0;
+                else stack.push_back({op.z, a});
+            } else if (op.x == OP_PUSH_TRANSLATE) {
+                // the enclosing bound keeps its extents under a translation: carry its area into the new frame
+                const double a = (stack.size() > base) ? stack.back().area : -1.0;
+                frame_base.push_back(stack.size());
+                if (a > 0.0) stack.push_back({(uint32_t)n, a});
+            } else if (op.x == OP_PUSH_ROTATE_Y) {
+                frame_base.push_back(stack.size());
+            } else if (op.x == OP_POP) {
+                if (!frame_base.empty()) { stack.resize(frame_base.back()); frame_base.pop_back(); }
+            }
+        }
+        std::vector<uint32_t> renum(n + 1, 0);
+        uint32_t next = 0;
+        for (size_t pc = 0; pc < n; ++pc) { renum[pc] = next; next += keep[pc]; }
+        renum[n] = next;
+        out.ops_pruned.clear();
+        if (next == n) return;  // nothing to drop: the packet scan uses `ops`
+        out.ops_pruned.reserve(next);
+        for (size_t pc = 0; pc < n; ++pc) {
+            if (!keep[pc]) continue;
+            uint4 op = out.ops[pc];
+            if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) op.z = renum[op.z];
+            out.ops_pruned.push_back(op);
+        }
+    }
+
     int run() {
         if (!sc) { fail(WRT_E_INVALID, "scene is NULL"); return code; }
         if (sc->abi_version != WRT_ABI_VERSION) { fail(WRT_E_INVALID, "wrt_scene.abi_version mismatch"); return code; }
@@ -390,6 +442,7 @@ struct Compiler {
         if (!compile_materials() || !compile_geometry() || !compile_lights()) return code;
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
+        prune_program();
         // transform chains in application order (outermost first), so the device needs no per-thread array
         out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
         for (size_t x = 0; x < out.xforms.size(); ++x) {

@@ -11,6 +11,7 @@ namespace wrt {
 
 struct CompiledScene {
     std::vector<uint4> ops;
+    std::vector<uint4> ops_pruned;  // `ops` minus the nodes that cannot cull (packet scan under WRT_CULL_TIGHT); empty = same as ops
     std::vector<BoxRef> boxes_ref;
     std::vector<BoxTight> boxes_tight;
     std::vector<Node2> nodes2;  // parallel to boxes_*: child-pair records of the bvh_node ops (ordered traversal)
