@@ -355,6 +355,84 @@ def test_full_size_cornell_config_properties(ctx, wrt, wro):
     sc.close()
 
 
+def _adversarial_rays(flat, rng, span):
+    """Rays built to sit on decision boundaries: aimed at quad edges and corners (exactly and a few ulps / 1e-9 / 1e-6
+    off), leaving from points ON quads and spheres (t = 0 against their own primitive, numerators of exactly 0),
+    axis-aligned and zero-component directions, tangents to spheres, far-away origins, tiny and huge directions."""
+    O, D = [], []
+    lo, hi = span
+    quads = [flat.quads[i] for i in range(flat.n_quads)]
+    spheres = [flat.spheres[i] for i in range(flat.n_spheres)]
+    offs = np.array([0.0, 1e-15, -1e-15, 1e-12, -1e-12, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4])
+    for q in quads:
+        s0, u, v = np.array(q.start[:]), np.array(q.u[:]), np.array(q.v[:])
+        n = np.array(q.normal[:])
+        for a, b in [(0, 0), (0, 1), (1, 0), (1, 1), (0, .5), (1, .5), (.5, 0), (.5, 1), (.5, .5), (0, .25), (.75, 1)]:
+            for da in offs:
+                p = s0 + (a + da) * u + (b + da) * v
+                for _ in range(3):
+                    o = rng.uniform(lo, hi, 3)
+                    O.append(o); D.append(p - o)
+                O.append(p); D.append(rng.normal(size=3))      # leave from the quad itself (bounce rays)
+                O.append(p); D.append(n * (1.0 if rng.random() < 0.5 else -1.0))
+                O.append(p); D.append(u + da * n)              # (nearly) in the quad's plane
+                e = np.zeros(3); e[rng.integers(3)] = rng.choice([-1.0, 1.0])
+                O.append(p); D.append(e)
+    for sp in spheres[:8]:
+        c, r = np.array(sp.center[:]), sp.radius
+        for _ in range(100):
+            w = rng.normal(size=3); w /= np.linalg.norm(w)
+            p = c + r * w
+            t = np.cross(w, rng.normal(size=3)); t /= np.linalg.norm(t)
+            o = p + t * rng.uniform(1, 500)
+            O.append(o); D.append(p - o)                                 # tangent
+            O.append(o); D.append(p + w * rng.choice(offs) * r - o)      # just inside / outside the silhouette
+            O.append(p); D.append(rng.normal(size=3))                    # from the surface
+            O.append(p); D.append(-w)                                    # through the centre from the surface
+            O.append(c + w * r * 0.5); D.append(rng.normal(size=3))      # from inside
+    for _ in range(1000):
+        o = rng.uniform(lo, hi, 3)
+        d = rng.normal(size=3)
+        d[rng.integers(3)] = 0.0
+        O.append(o); D.append(d)
+        O.append(o * 1e4); D.append(-o + rng.normal(size=3))            # far origin looking back at the scene
+        O.append(o); D.append(d * 1e-12)
+        O.append(o); D.append(d * 1e12)
+    return np.ascontiguousarray(O, dtype=np.float64), np.ascontiguousarray(D, dtype=np.float64)
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "emissive", "shrek_quads", "earth", "balls"])
+def test_closest_hit_on_boundary_rays(ctx, wrt, wro, images, name):
+    """Edge, corner, silhouette, on-surface and degenerate-direction rays — the rays on which closed-vs-open intervals, the
+    1e-8 parallel-plane cut, the tmin cut and the culling rule decide the result.  WRT_CULL_REFERENCE (packet and per
+    lane) returns the oracle's hit bit for bit, including the hits the reference's own box test loses on such rays;
+    WRT_CULL_TIGHT returns the brute-force closest hit (the oracle with culling disabled) bit for bit."""
+    sc = wro.OracleScene(name, seed=1, images=images)
+    flat = sc.flatten()
+    ctx.upload_scene(flat)
+    rng = np.random.default_rng(11)
+    span = {"cornell_box": (0, 555), "emissive": (-30, 30), "shrek_quads": (-6, 6), "earth": (-30, 30), "balls": (-12, 12)}[name]
+    o, d = _adversarial_rays(flat, rng, span)
+    want_ref = sc.trace_rays(o, d)
+    sc.set_no_cull(True)
+    want_brute = sc.trace_rays(o, d)
+    sc.set_no_cull(False)
+    assert (want_brute["prim_id"] != NONE).mean() > 0.1
+    # the reference's box test is not conservative on a few of these rays (x/y-only, per-axis, on-boundary origins)
+    assert (want_ref["prim_id"] != want_brute["prim_id"]).mean() < 0.05
+    cases = [(wrt.WRT_CULL_REFERENCE, want_ref), (wrt.WRT_CULL_REFERENCE | wrt.WRT_TRAV_FORCE_LANE, want_ref),
+             (wrt.WRT_CULL_REFERENCE | wrt.WRT_TRAV_FORCE_PACKET, want_ref),
+             (wrt.WRT_CULL_TIGHT, want_brute), (wrt.WRT_CULL_TIGHT | wrt.WRT_TRAV_FORCE_PACKET, want_brute),
+             (wrt.WRT_CULL_TIGHT | wrt.WRT_TRAV_FORCE_LANE, want_brute)]
+    for mode, want in cases:
+        got = ctx.trace_rays(o, d, cull_mode=mode)
+        np.testing.assert_array_equal(got["prim_id"], want["prim_id"], err_msg=hex(mode))
+        np.testing.assert_array_equal(got["t"].view(np.uint64), want["t"].view(np.uint64), err_msg=hex(mode))
+        np.testing.assert_array_equal(got["point"].view(np.uint64), want["point"].view(np.uint64), err_msg=hex(mode))
+        np.testing.assert_array_equal(got["normal"].view(np.uint64), want["normal"].view(np.uint64), err_msg=hex(mode))
+    sc.close()
+
+
 # ---- engines and traversal variants: all must agree bit for bit ---------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cornell_box", "emissive", "balls", "rtw_final", "earth", "shrek_quads"])
 def test_wavefront_engine_is_bit_identical_to_megakernel(ctx, wrt, wro, images, name):

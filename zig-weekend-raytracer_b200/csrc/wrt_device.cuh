@@ -719,12 +719,12 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
         } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
             apply_xform(S.xforms[op.y], o, d);
             xf = op.y;
-            cull.set_ray(o, d);
+            if (!op.z) cull.set_ray(o, d);  // z = 1 (pruned program): no box test before the next transform op
             ++pc;
         } else if (op.x == OP_POP) {
             xf = op.y;
             ray_in_xform(S, xf, wo, wd, o, d);
-            cull.set_ray(o, d);
+            if (!op.z) cull.set_ray(o, d);
             ++pc;
         } else {  // OP_END
             break;

@@ -373,12 +373,17 @@ struct Compiler {
         return true;
     }
 
-    // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` minus the nodes whose conservative box
-    // cannot cull anything their nearest kept ancestor has not culled already — surface area >= 90 % of that ancestor's,
-    // compared within one coordinate frame (a translation keeps the extents, a rotation starts afresh).  The Cornell box
-    // is the type case: its BVH puts one wall in each half, so 7 of its 8 bvh_node boxes are the whole room and every ray
-    // passes them.  Tight boxes are conservative, so dropping a test never changes a result; skip links are re-indexed.
-    // WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
+    // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` with the work removed that cannot pay for
+    // itself when 32 rays share one program counter.  Tight boxes are conservative, so dropping a box test never changes a
+    // result; WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
+    //   * nodes whose box has >= 50 % of the surface area of their nearest kept ancestor (same coordinate frame; a
+    //     translation keeps the extents, a rotation starts afresh): a subtree is skipped only when ALL lanes miss its box,
+    //     which for so large a box practically never happens.  Cornell box: its BVH puts one wall in each half, so 7 of its
+    //     8 bvh_node boxes are (nearly) the whole room.  The root is always kept (it is what stops rays that miss the scene).
+    //   * a POP directly followed by another POP (the outer one recomputes the ray from the world ray anyway);
+    //   * transform ops are flagged (z = 1) when no box test runs before the next transform op: the scan then skips the
+    //     binary32 culler set-up (3 reciprocals + conversions) for that frame.  Safe on every execution path: a node that is
+    //     reached by skipping a subtree sees the culler its subtree's root node was tested with, in the same frame.
     void prune_program() {
         const size_t n = out.ops.size();
         struct Enclosing { uint32_t end; double area; };
@@ -391,13 +396,15 @@ struct Compiler {
             if (!(dx >= 0.0 && dy >= 0.0 && dz >= 0.0)) return -1.0;  // empty / inverted: keep the test, it culls everything
             return 2.0 * (dx * dy + dy * dz + dz * dx);
         };
+        auto is_xform = [](uint32_t kind) { return kind == OP_PUSH_TRANSLATE || kind == OP_PUSH_ROTATE_Y || kind == OP_POP; };
+        auto is_node = [](uint32_t kind) { return kind == OP_NODE || kind == OP_NODE_TIGHT_ONLY; };
         for (size_t pc = 0; pc < n; ++pc) {
             const uint4 op = out.ops[pc];
             const size_t base = frame_base.empty() ? 0 : frame_base.back();
             while (stack.size() > base && stack.back().end <= pc) stack.pop_back();
-            if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) {
+            if (is_node(op.x)) {
                 const double a = area_of(op.y);
-                if (stack.size() > base && a >= 0.0 && stack.back().area > 0.0 && a >= 0.9 * stack.back().area) keep[pc] = 0;
+                if (stack.size() > base && a >= 0.0 && stack.back().area > 0.0 && a >= 0.5 * stack.back().area) keep[pc] = 0;
                 else stack.push_back({op.z, a});
             } else if (op.x == OP_PUSH_TRANSLATE) {
                 // the enclosing bound keeps its extents under a translation: carry its area into the new frame
@@ -410,19 +417,37 @@ struct Compiler {
                 if (!frame_base.empty()) { stack.resize(frame_base.back()); frame_base.pop_back(); }
             }
         }
+        // POP, POP -> POP
+        for (size_t pc = 0; pc < n; ++pc) {
+            if (!keep[pc] || out.ops[pc].x != OP_POP) continue;
+            size_t nx = pc + 1;
+            while (nx < n && !keep[nx]) ++nx;
+            if (nx < n && out.ops[nx].x == OP_POP) keep[pc] = 0;
+        }
         std::vector<uint32_t> renum(n + 1, 0);
         uint32_t next = 0;
         for (size_t pc = 0; pc < n; ++pc) { renum[pc] = next; next += keep[pc]; }
         renum[n] = next;
         out.ops_pruned.clear();
-        if (next == n) return;  // nothing to drop: the packet scan uses `ops`
         out.ops_pruned.reserve(next);
         for (size_t pc = 0; pc < n; ++pc) {
             if (!keep[pc]) continue;
             uint4 op = out.ops[pc];
-            if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) op.z = renum[op.z];
+            if (is_node(op.x)) op.z = renum[op.z];
             out.ops_pruned.push_back(op);
         }
+        bool changed = next != n;
+        for (size_t pc = 0; pc < out.ops_pruned.size(); ++pc) {
+            uint4& op = out.ops_pruned[pc];
+            if (!is_xform(op.x)) continue;
+            size_t nx = pc + 1;
+            while (nx < out.ops_pruned.size() && !is_node(out.ops_pruned[nx].x) && !is_xform(out.ops_pruned[nx].x) &&
+                   out.ops_pruned[nx].x != OP_END) ++nx;
+            const bool culler_used = nx < out.ops_pruned.size() && is_node(out.ops_pruned[nx].x);
+            op.z = culler_used ? 0u : 1u;
+            changed = changed || !culler_used;
+        }
+        if (!changed) out.ops_pruned.clear();  // identical to `ops`: the packet scan uses that
     }
 
     int run() {
