@@ -8,6 +8,7 @@
 //   * primitive ids = first-visit DFS order.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -175,6 +176,10 @@ struct Compiler {
 
     // ---- program emission ------------------------------------------------------------------------------
     uint32_t nest = 0;  // current nesting of bvh_node / instance ops (bounds the ordered traversal's stack)
+    struct BvhItem { uint32_t start, end; Box3 box; };                       // a leaf entity of a reference BVH: its op range + tight box
+    struct BvhRoot { uint32_t record; uint32_t nest; std::vector<BvhItem> items; };
+    std::vector<BvhItem>* cur_items = nullptr;  // != null while emitting below a bvh_node
+    std::vector<BvhRoot> bvh_roots;             // every reference BVH, for rebuild_trees()
     bool emit(uint32_t id, uint32_t xf, uint32_t xf_depth) {
         if (!check_entity(id, "emit")) return false;
         struct Nest { uint32_t& n; uint32_t& mx; bool on; Nest(uint32_t& n_, uint32_t& mx_, bool on_) : n(n_), mx(mx_), on(on_) { if (on) { ++n; if (n > mx) mx = n; } } ~Nest() { if (on) --n; } };
@@ -207,13 +212,34 @@ struct Compiler {
                 const uint32_t box = push_box(e, tb);
                 const size_t at = out.ops.size();
                 out.ops.push_back(make_uint4(OP_NODE, box, 0, 0));
+                // the leaf entities below this BVH's root are collected for rebuild_trees()
+                const bool is_root = (cur_items == nullptr);
+                std::vector<BvhItem> root_items;
+                if (is_root) cur_items = &root_items;
+                auto emit_child = [&](uint32_t child) -> bool {
+                    if (!check_entity(child, "bvh_node child")) return false;
+                    if (sc->entities[child].kind == WRT_ENT_BVH_NODE) return emit(child, xf, xf_depth);
+                    std::vector<BvhItem>* const items = cur_items;
+                    cur_items = nullptr;  // a BVH nested inside this leaf (instance, collection) is a tree of its own
+                    BvhItem it;
+                    it.start = (uint32_t)out.ops.size();
+                    const bool child_ok = emit(child, xf, xf_depth) && tight_box(child, it.box);
+                    it.end = (uint32_t)out.ops.size();
+                    cur_items = items;
+                    if (child_ok) items->push_back(it);
+                    return child_ok;
+                };
                 const uint32_t l_start = (uint32_t)out.ops.size();
-                ok = emit(e.a, xf, xf_depth);
+                ok = emit_child(e.a);
                 const uint32_t r_start = (uint32_t)out.ops.size();
                 // span == 1 nodes hold the same child twice (entity.zig:231-233); the second visit cannot change the result
-                if (ok && e.b != e.a) ok = emit(e.b, xf, xf_depth);
+                if (ok && e.b != e.a) ok = emit_child(e.b);
                 const uint32_t end = (uint32_t)out.ops.size();
                 out.ops[at].z = end;
+                if (is_root) {
+                    cur_items = nullptr;
+                    if (ok) bvh_roots.push_back(BvhRoot{box, nest, std::move(root_items)});
+                }
                 if (ok) {  // child-pair record for the ordered traversal: both children's boxes + where they live in the program
                     Node2 n2;
                     Box3 lb, rb;
@@ -373,6 +399,119 @@ struct Compiler {
         return true;
     }
 
+    // ---- ordered-traversal trees ------------------------------------------------------------------------
+    // The ordered traversal (wrt_device.cuh, Trav) only needs SOME binary tree over the leaf entities of each reference
+    // BVH: closest hit and tie rule are properties of the primitives and their DFS positions, not of the tree.  The
+    // reference splits at the median of a RANDOM axis (entity.zig:226-259); here each BVH is rebuilt over the same leaves
+    // with a binned surface-area heuristic on the tight boxes (3 axes x 16 bins, median fallback, depth-capped), which
+    // roughly halves the nodes a ray visits on the 2^20-primitive scene.  `ops`, the reference boxes and everything
+    // WRT_CULL_REFERENCE reads keep the reference topology.  WRT_REFERENCE_TREE=1 keeps it for the ordered traversal too.
+    static double half_area(const Box3& b) {
+        if (!b.valid()) return 0.0;
+        const double dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    static void set_child(Node2& n, bool left, const Box3& b, uint32_t desc, uint32_t end) {
+        const BoxTight p = padded(b);
+        if (left) {
+            n.lmin[0] = p.min_x; n.lmin[1] = p.min_y; n.lmin[2] = p.min_z; n.l_desc = desc;
+            n.lmax[0] = p.max_x; n.lmax[1] = p.max_y; n.lmax[2] = p.max_z; n.l_end = end;
+        } else {
+            n.rmin[0] = p.min_x; n.rmin[1] = p.min_y; n.rmin[2] = p.min_z; n.r_desc = desc;
+            n.rmax[0] = p.max_x; n.rmax[1] = p.max_y; n.rmax[2] = p.max_z; n.r_end = end;
+        }
+    }
+    // builds the subtree over items[lo, hi) (hi - lo >= 2) into record `rec`; returns its depth in records
+    uint32_t build_sah(std::vector<BvhItem>& items, size_t lo, size_t hi, uint32_t rec, uint32_t level) {
+        constexpr int kBins = 16;
+        auto centroid = [](const BvhItem& it, int k) { return it.box.valid() ? 0.5 * (it.box.mn[k] + it.box.mx[k]) : 0.0; };
+        Box3 cb;
+        cb.reset();
+        for (size_t i = lo; i < hi; ++i) { double c[3] = {centroid(items[i], 0), centroid(items[i], 1), centroid(items[i], 2)}; cb.grow(c); }
+        size_t mid = lo;
+        double best_cost = std::numeric_limits<double>::infinity();
+        int best_axis = -1, best_bin = 0;
+        if (level <= 30) {
+            for (int axis = 0; axis < 3; ++axis) {
+                const double ext = cb.mx[axis] - cb.mn[axis];
+                if (!(ext > 0.0)) continue;
+                Box3 bin_box[kBins];
+                size_t bin_n[kBins] = {};
+                for (auto& b : bin_box) b.reset();
+                const double scale = kBins / ext;
+                for (size_t i = lo; i < hi; ++i) {
+                    int b = (int)((centroid(items[i], axis) - cb.mn[axis]) * scale);
+                    b = std::min(std::max(b, 0), kBins - 1);
+                    ++bin_n[b];
+                    if (items[i].box.valid()) bin_box[b].grow(items[i].box);
+                }
+                double right_area[kBins];
+                size_t right_n[kBins];
+                Box3 acc;
+                acc.reset();
+                size_t n = 0;
+                for (int b = kBins - 1; b > 0; --b) { acc.grow(bin_box[b]); n += bin_n[b]; right_area[b] = half_area(acc); right_n[b] = n; }
+                acc.reset();
+                n = 0;
+                for (int b = 0; b + 1 < kBins; ++b) {  // split after bin b
+                    acc.grow(bin_box[b]);
+                    n += bin_n[b];
+                    if (n == 0 || right_n[b + 1] == 0) continue;
+                    const double cost = half_area(acc) * (double)n + right_area[b + 1] * (double)right_n[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                }
+            }
+        }
+        if (best_axis >= 0) {
+            const double ext = cb.mx[best_axis] - cb.mn[best_axis];
+            const double scale = kBins / ext, base = cb.mn[best_axis];
+            auto it = std::partition(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)hi, [&](const BvhItem& x) {
+                int b = (int)((centroid(x, best_axis) - base) * scale);
+                b = std::min(std::max(b, 0), kBins - 1);
+                return b <= best_bin;
+            });
+            mid = (size_t)(it - items.begin());
+        }
+        if (mid == lo || mid == hi) {  // no usable SAH split (coincident centroids, depth cap): median of the widest axis
+            int axis = 0;
+            for (int k = 1; k < 3; ++k) if (cb.mx[k] - cb.mn[k] > cb.mx[axis] - cb.mn[axis]) axis = k;
+            mid = lo + (hi - lo) / 2;
+            std::nth_element(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)mid, items.begin() + (ptrdiff_t)hi,
+                             [&](const BvhItem& a, const BvhItem& b) { return centroid(a, axis) < centroid(b, axis); });
+        }
+        uint32_t depth = 1;
+        Node2 n;
+        std::memset(&n, 0, sizeof n);
+        for (int side = 0; side < 2; ++side) {
+            const size_t a = side == 0 ? lo : mid, b = side == 0 ? mid : hi;
+            Box3 bb;
+            bb.reset();
+            for (size_t i = a; i < b; ++i) if (items[i].box.valid()) bb.grow(items[i].box);
+            if (b - a == 1) {
+                set_child(n, side == 0, bb, items[a].start, items[a].end);
+            } else {
+                Node2 none;
+                std::memset(&none, 0, sizeof none);
+                none.l_desc = none.r_desc = WRT_NONE;
+                out.nodes2.push_back(none);
+                const uint32_t child = (uint32_t)(out.nodes2.size() - 1);
+                depth = std::max(depth, 1 + build_sah(items, a, b, child, level + 1));
+                set_child(n, side == 0, bb, 0x80000000u | child, 0);
+            }
+        }
+        out.nodes2[rec] = n;
+        return depth;
+    }
+    void rebuild_trees() {
+        const char* keep = std::getenv("WRT_REFERENCE_TREE");
+        if (keep && keep[0] == '1') return;
+        for (BvhRoot& r : bvh_roots) {
+            if (r.items.size() < 2) continue;  // a single leaf: the reference's record is already minimal
+            const uint32_t depth = build_sah(r.items, 0, r.items.size(), r.record, 1);
+            out.max_nesting = std::max(out.max_nesting, r.nest + depth);
+        }
+    }
+
     // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` with the work removed that cannot pay for
     // itself when 32 rays share one program counter.  Tight boxes are conservative, so dropping a box test never changes a
     // result; WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
@@ -386,6 +525,8 @@ struct Compiler {
     //     reached by skipping a subtree sees the culler its subtree's root node was tested with, in the same frame.
     void prune_program() {
         const size_t n = out.ops.size();
+        out.ops_pruned.clear();
+        if (n > 1024) return;  // far beyond WRT_PACKET_MAX_OPS: the packet scan is never chosen for such a program
         struct Enclosing { uint32_t end; double area; };
         std::vector<Enclosing> stack;      // kept nodes around the current op, innermost last
         std::vector<size_t> frame_base;    // stack height at each open PUSH (ancestors below it live in another frame)
@@ -467,6 +608,7 @@ struct Compiler {
         if (!compile_materials() || !compile_geometry() || !compile_lights()) return code;
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
+        rebuild_trees();
         prune_program();
         // transform chains in application order (outermost first), so the device needs no per-thread array
         out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
