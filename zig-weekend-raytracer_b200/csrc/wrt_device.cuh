@@ -329,7 +329,7 @@ template <>
 struct Culler<WRT_CULL_TIGHT> {
     float inv_x, inv_y, inv_z;   // 1 / d
     float oi_x, oi_y, oi_z;      // o / d
-    float err_x, err_y, err_z;   // |o / d| * 2^-21: absolute slab-distance error of this ray, per axis
+    float err;                   // max_k |o_k / d_k| * 2^-21: absolute slab-distance error of this ray (the largest axis' bound serves all three)
     static __device__ __forceinline__ float safe_inv(double v) {
         float f = (float)v;
         // a zero / denormal component would make inv infinite and b*inv - o*inv an inf - inf NaN
@@ -339,7 +339,7 @@ struct Culler<WRT_CULL_TIGHT> {
     __device__ __forceinline__ void set_ray(d3 ro, d3 rd) {
         inv_x = safe_inv(rd.x); inv_y = safe_inv(rd.y); inv_z = safe_inv(rd.z);
         oi_x = (float)ro.x * inv_x; oi_y = (float)ro.y * inv_y; oi_z = (float)ro.z * inv_z;
-        err_x = fabsf(oi_x) * 4.8e-7f; err_y = fabsf(oi_y) * 4.8e-7f; err_z = fabsf(oi_z) * 4.8e-7f;
+        err = fmaxf(fmaxf(fabsf(oi_x), fabsf(oi_y)), fabsf(oi_z)) * 4.8e-7f;
     }
     __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
         const float4* p = reinterpret_cast<const float4*>(S.boxes_tight + box);
@@ -347,12 +347,9 @@ struct Culler<WRT_CULL_TIGHT> {
         const float ax = fmaf(lo4.x, inv_x, -oi_x), bx = fmaf(hi4.x, inv_x, -oi_x);
         const float ay = fmaf(lo4.y, inv_y, -oi_y), by = fmaf(hi4.y, inv_y, -oi_y);
         const float az = fmaf(lo4.z, inv_z, -oi_z), bz = fmaf(hi4.z, inv_z, -oi_z);
-        const float nx = fminf(ax, bx) - err_x, fx = fmaxf(ax, bx) + err_x;
-        const float ny = fminf(ay, by) - err_y, fy = fmaxf(ay, by) + err_y;
-        const float nz = fminf(az, bz) - err_z, fz = fmaxf(az, bz) + err_z;
         const float t_lo = __double2float_rd(tmin), t_hi = __double2float_ru(tmax);
-        const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
-        const float hi = fminf(fminf(fx, fy), fminf(fz, t_hi));
+        const float lo = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - err, t_lo);
+        const float hi = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) + err, t_hi);
         return hi * 1.000002f + 1e-30f >= lo;  // relative slack for the rounding of inv (|t| * 2^-21 on either side)
     }
     // same test on an explicit box; also returns the (conservative) entry distance for near-first ordering
@@ -361,11 +358,8 @@ struct Culler<WRT_CULL_TIGHT> {
         const float ax = fmaf(mnx, inv_x, -oi_x), bx = fmaf(mxx, inv_x, -oi_x);
         const float ay = fmaf(mny, inv_y, -oi_y), by = fmaf(mxy, inv_y, -oi_y);
         const float az = fmaf(mnz, inv_z, -oi_z), bz = fmaf(mxz, inv_z, -oi_z);
-        const float nx = fminf(ax, bx) - err_x, fx = fmaxf(ax, bx) + err_x;
-        const float ny = fminf(ay, by) - err_y, fy = fmaxf(ay, by) + err_y;
-        const float nz = fminf(az, bz) - err_z, fz = fmaxf(az, bz) + err_z;
-        const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
-        const float hi = fminf(fminf(fx, fy), fminf(fz, t_hi));
+        const float lo = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - err, t_lo);
+        const float hi = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) + err, t_hi);
         t_entry = lo;
         return hi * 1.000002f + 1e-30f >= lo;
     }
@@ -476,8 +470,7 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 // unless a later one is a quad, in which case the last such quad wins.  Ops are numbered in DFS order, so tracking
 // (first op, last quad op) of the minimal-t set reproduces that rule under any visiting order.
 #define WRT_STACK_DEPTH 48
-// Resumable form: the traversal state lives in a struct so a warp can stop stepping when too few of its lanes are still
-// traversing, hand the finished lanes new rays, and resume the others where they were (render_kernel_lane).
+// The traversal state.
 struct Trav {
     double best_t;
     d3 o, d;  // ray in the current transform context
@@ -501,10 +494,10 @@ __device__ __forceinline__ void trav_init(const DeviceScene& S, Trav& T, d3 wo, 
     T.node = WRT_NONE;              // != NONE: descend from this child-pair record instead
 }
 
-// One step (one child-pair record, one op, or one pop).  Returns true when the traversal is complete.
-__device__ __forceinline__ bool trav_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
-                                          double tmin, double tmax) {
-    if (T.node != WRT_NONE) {
+// One child-pair record: test both children, go to the nearer one that is hit, defer the other.  Leaves T.node set (next
+// record), or a leaf op range in (T.pc, T.end), or an empty range (nothing hit: the caller pops).
+__device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+    {
         const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
         const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
         const float t_hi = __double2float_ru(T.best_t);
@@ -528,10 +521,15 @@ __device__ __forceinline__ bool trav_step(const DeviceScene& S, Trav& T, uint4* 
         if (go_desc != WRT_NONE) {
             if (go_desc & 0x80000000u) { T.node = go_desc & 0x7FFFFFFFu; }
             else { T.node = WRT_NONE; T.pc = go_desc; T.end = go_end; }
-            return false;
+            return;
         }
-        T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: pop below
+        T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
     }
+}
+
+// One pop or one op of the current leaf range.  Returns true when the traversal is complete.
+__device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
+                                               double tmin, double tmax) {
     if (T.pc >= T.end) {  // range exhausted: pop
         while (T.sp > 0) {
             const uint4 e = stack[--T.sp];
@@ -629,7 +627,12 @@ __device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3
     Trav T;
     uint4 stack[WRT_STACK_DEPTH];  // {desc | first op, end op, xform, entry distance bits}
     trav_init(S, T, wo, wd, time, tmin, tmax);
-    while (!trav_step(S, T, stack, wo, wd, time, tmin, tmax)) {}
+    // "while-while": every lane first descends through box records until it stands on a leaf range (cheap binary32 steps),
+    // then the lanes of the warp run their binary64 primitive tests together
+    for (;;) {
+        while (T.node != WRT_NONE) trav_node_step(S, T, stack);
+        if (trav_leaf_step(S, T, stack, wo, wd, time, tmin, tmax)) break;
+    }
     return trav_result(T);
 }
 

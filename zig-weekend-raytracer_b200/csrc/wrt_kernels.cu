@@ -395,109 +395,6 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
     }
 }
 
-// render_kernel for large programs (per-lane ordered traversal, WRT_CULL_TIGHT).  On a 2^20-primitive scene one closest-hit
-// query takes anywhere from tens to thousands of node visits, so a warp that waits for its slowest lane runs at ~3 active
-// threads per instruction (profiles/README.md).  Here traversal is resumable: the warp steps all traversing lanes together
-// and LEAVES the stepping loop as soon as a quarter of them are done; those lanes shade, get their next ray (or a fresh
-// camera sample) and re-enter, the others resume where they stopped (terminated-ray replacement, Aila & Laine 2009).
-// Same functions, same arithmetic, same per-lane sample order as render_kernel: the frame is bit-identical.
-__global__ void __launch_bounds__(WRT_RENDER_BLOCK, WRT_RENDER_MIN_BLOCKS) render_kernel_lane(DeviceScene S, double* __restrict__ accum,
-                                                                                              unsigned long long* __restrict__ counters) {
-    const RenderConstants& rc = c_rc;
-    const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long n_rays = 0, n_paths = 0;
-    const double scale = 1.0 / (double)rc.spp;
-    const bool dof = rc.dof != 0;
-    const bool need_time = S.has_moving != 0;
-    Rng rng;
-    rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
-    uint4 stack[WRT_STACK_DEPTH];
-    unsigned long long n_steps = 0;
-
-    for (;;) {
-        unsigned long long job = 0;
-        if (lane == 0) job = atomicAdd(&counters[0], 1ull);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= rc.total_jobs) break;
-        const uint32_t blocks_per_chunk = rc.n_rows_local * rc.n_col_blocks;
-        const uint32_t chunk = (uint32_t)(job / blocks_per_chunk);
-        const uint32_t rem = (uint32_t)(job % blocks_per_chunk);
-        const uint32_t local_row = rem / rc.n_col_blocks;
-        const uint32_t col = (rem % rc.n_col_blocks) * 32u + lane;
-        const uint32_t row = rc.row_shard_index + local_row * rc.row_shard_count;
-        const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
-        const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
-        const bool lane_active = col < rc.width;
-
-        d3 color = mk(0, 0, 0);
-        uint32_t s = s_first;
-        bool alive = false;       // the lane carries a path
-        bool traversing = false;  // ... whose current ray is still being traced
-        uint32_t depth_left = 0;
-        Ray ray;
-        ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
-        d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
-        Trav T;
-        rng.pixel = row * rc.width + col;
-        rng.sample = 0;
-
-        for (;;) {
-            if (!traversing) {
-                if (alive) {  // a traversal just finished: shade it
-                    ++n_rays;
-                    const ClosestHit ch = trav_result(T);
-                    const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
-                    --depth_left;
-                    if (!cont || depth_left == 0) {
-                        if (cont) L = L + beta * 0.0;
-                        color = color + L * scale;
-                        alive = false;
-                        ++s;
-                    }
-                }
-                if (!alive && lane_active && s < s_last) {
-                    rng.sample = s;
-                    ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
-                    beta = mk(1, 1, 1); L = mk(0, 0, 0);
-                    depth_left = rc.max_depth;
-                    alive = depth_left > 0;
-                    ++n_paths;
-                    if (!alive) ++s;
-                }
-                if (alive) {
-                    trav_init(S, T, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
-                    traversing = true;
-                }
-            }
-            const unsigned entered = __ballot_sync(0xffffffffu, traversing);
-            if (entered == 0) {
-                if (!__any_sync(0xffffffffu, lane_active && s < s_last)) break;
-                continue;
-            }
-            // step until a quarter of the lanes that entered have finished (at least one)
-            const int keep = (__popc(entered) * 3) / 4;
-            for (;;) {
-                if (traversing) { traversing = !trav_step(S, T, stack, ray.o, ray.d, ray.time, 1e-4, CUDART_INF); ++n_steps; }
-                if (__popc(__ballot_sync(0xffffffffu, traversing)) <= keep) break;
-            }
-        }
-        if (lane_active) {
-            double* slot = accum + ((size_t)chunk * rc.n_rows_local * rc.width + (size_t)local_row * rc.width + col) * 3;
-            slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
-        n_paths += __shfl_down_sync(0xffffffffu, n_paths, off);
-        n_steps += __shfl_down_sync(0xffffffffu, n_steps, off);
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[1], n_rays);
-        atomicAdd(&counters[2], n_paths);
-        atomicAdd(&counters[3], n_steps);
-    }
-}
-
 // Phase-synchronous variant of render_kernel: ONE block of 16 warps per SM, and all 16 warps move through the three phases
 // of an iteration (regenerate | closest hit | shade) together, separated by block barriers.  The integrator is the same,
 // the arithmetic is the same, the frame is bit-identical; what changes is the instruction working set: at any time the
@@ -1123,17 +1020,8 @@ static cudaError_t dispatch(uint32_t cull_mode, bool packet, F&& f) {
     return cudaGetLastError();
 }
 
-// The resumable lane kernel pays for its larger per-thread state; it wins once traversal lengths vary by orders of
-// magnitude between rays, i.e. on large programs (measured: 2^20 primitives yes, 484 spheres no).
-static bool use_lane_kernel(const DeviceScene& S, uint32_t cull_mode, bool packet) {
-    return !packet && cull_mode == WRT_CULL_TIGHT && S.use_ordered && S.n_ops > WRT_LANE_KERNEL_MIN_OPS;
-}
 cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream) {
-    if (use_lane_kernel(S, cull_mode, packet)) {
-        render_kernel_lane<<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
-        return cudaGetLastError();
-    }
     return dispatch(cull_mode, packet, [&](auto c, auto t) {
         render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
     });
@@ -1161,8 +1049,6 @@ cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool pa
 }
 cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm) {
     cudaError_t err = cudaSuccess;
-    if (use_lane_kernel(S, cull_mode, packet))
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel_lane, WRT_RENDER_BLOCK, 0);
     dispatch(cull_mode, packet, [&](auto c, auto t) {
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<decltype(c)::value, decltype(t)::value>,
                                                             WRT_RENDER_BLOCK, 0);

@@ -17,8 +17,6 @@
 #define WRT_SYNC_BLOCK 512  // phase-synchronous variant: one block of 16 warps per SM
 // Programs up to this many ops are scanned with the warp-uniform packet traversal.
 #define WRT_PACKET_MAX_OPS 96u
-// Programs larger than this use the resumable per-lane kernel (terminated-ray replacement inside the traversal loop).
-#define WRT_LANE_KERNEL_MIN_OPS 65536u
 
 namespace wrt {
 
