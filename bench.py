@@ -280,6 +280,7 @@ def main():
         return st.rays, st.paths, st.render_ms, st.kernel_ms, g_ms, st.kernel_launches
 
     fp64_peak = ctx.fp64_issue_peak() if rank == 0 else 0.0
+    fp32_peak = ctx.fp32_issue_peak() if rank == 0 else 0.0
 
     for _ in range(args.warmup):
         device_step()
@@ -369,7 +370,8 @@ def main():
                      "note": "cache-resident scene: HBM is not the binding bound here, see roofline_issue"},
         "roofline_issue": {"bound": "fp64_issue", "achieved": ach_issue / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64 instr/s",
                            "frac": (ach_issue / fp64_peak) if fp64_peak else None, "algorithmic_fp64_instr_per_ray": wl["f_ray"],
-                           "peak_source": "DFMA micro-kernel measured live (wrt_fp64_issue_peak)"},
+                           "peak_source": "DFMA micro-kernel measured live (wrt_fp64_issue_peak)",
+                           "fp32_issue_peak": fp32_peak / 1e9, "fp32_note": "FFMA micro-kernel (wrt_fp32_issue_peak): the pipe the box tests run on"},
     }
     if not args.no_cpu_baseline and n_gpus == 1:
         spp_s = cpu_sample_spp(wl, args.cpu_sample_spp)

@@ -278,6 +278,8 @@ WRT_API int wrt_get_stats(const wrt_ctx* ctx, wrt_stats* out);
 /* Measures the device's binary64 FMA issue rate (thread-level DFMA per second) with a micro-kernel: the denominator of
  * the issue-bound roofline for the cache-resident configs. */
 WRT_API int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second);
+/* The same probe on the binary32 pipe (the conservative culler runs there). */
+WRT_API int wrt_fp32_issue_peak(wrt_ctx* ctx, double* fma_per_second);
 
 #ifdef __cplusplus
 }

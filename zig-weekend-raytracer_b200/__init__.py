@@ -25,7 +25,7 @@ from .abi import Camera, Params, Scene, Stats
 ABI_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_upload_scene", "wrt_render",
     "wrt_render_device", "wrt_encode_rgb8", "wrt_primary_hits", "wrt_trace_rays", "wrt_sobol_pixel_samples",
-    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak",
+    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak",
 ]
 
 
@@ -59,6 +59,7 @@ def _load() -> C.CDLL:
     lib.wrt_sobol_dimension_samples.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp]
     lib.wrt_get_stats.argtypes = [vp, vp]
     lib.wrt_fp64_issue_peak.argtypes = [vp, vp]
+    lib.wrt_fp32_issue_peak.argtypes = [vp, vp]
     for name in ABI_SYMBOLS:
         if name not in ("wrt_destroy", "wrt_last_error", "wrt_abi_version"):
             getattr(lib, name).restype = C.c_int
@@ -116,6 +117,12 @@ class Context:
         """Measured binary64 FMA issue rate of the device, thread-level FMAs per second."""
         out = C.c_double()
         self._check(lib.wrt_fp64_issue_peak(self._h, C.byref(out)))
+        return out.value
+
+    def fp32_issue_peak(self) -> float:
+        """Measured binary32 FMA issue rate of the device, thread-level FMAs per second."""
+        out = C.c_double()
+        self._check(lib.wrt_fp32_issue_peak(self._h, C.byref(out)))
         return out.value
 
     @staticmethod

@@ -352,6 +352,21 @@ static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
     t.b_bytes = 0;
     while (t.b_bytes < 8 && (b_mask >> (8 * t.b_bytes)) != 0) ++t.b_bytes;
     if (t.b_bytes > 7) return ctx->fail(WRT_E_LIMIT, "Sobol index exceeds 56 bits");
+    // increments of the dims 0/1 sample bits for s -> s + 1 (wrt_device.cuh: sobol_pixel_bits_next): the bits of the index
+    // of "sample" 2^(k+1) - 1 in pixel (0, 0) — everything below is linear over GF(2), so the pixel term cancels
+    for (int k = 0; k < 32; ++k) {
+        const uint64_t q = (k == 31) ? 0xFFFFFFFFull : ((1ull << (k + 1)) - 1);
+        uint64_t index = q;
+        if (t.log2_scale > 0) {
+            index = q << (2 * t.log2_scale);
+            uint64_t delta = 0;
+            for (int c = 0; c < 52; ++c) if ((q >> c) & 1) delta ^= t.vdc[c];
+            for (int c = 0; c < 52; ++c) if ((delta >> c) & 1) index ^= t.vdc_inv[c];
+        }
+        uint32_t v0 = 0, v1 = 0;
+        for (int c = 0; c < 52; ++c) if ((index >> c) & 1) { v0 ^= t.dim0[c]; v1 ^= t.dim1[c]; }
+        t.inc0[k] = v0; t.inc1[k] = v1;
+    }
     CU(ctx->d_sobol_lut.upload(lut, ctx->stream));
     t.lut = ctx->d_sobol_lut.p;
     CU(wrt::upload_sobol_tables(t, ctx->stream));
@@ -725,23 +740,24 @@ extern "C" int wrt_sobol_dimension_samples(wrt_ctx* ctx, const uint64_t* sobol_i
     return ret;
 }
 
-extern "C" int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second) {
+static int issue_peak(wrt_ctx* ctx, double* fma_per_second, bool fp32) {
     if (!ctx) return WRT_E_INVALID;
     int rc_ = bind_device(ctx);
     if (rc_) return rc_;
     if (!fma_per_second) return ctx->fail(WRT_E_INVALID, "fma_per_second is NULL");
     const uint32_t block = 256, grid = (uint32_t)ctx->sm_count * 8, iters = 1u << 16;
+    auto launch = fp32 ? wrt::launch_fp32_peak : wrt::launch_fp64_peak;
     DevBuf<double> d_out;
     int ret = WRT_OK;
     do {
         cudaError_t e;
 #define TRY(x) if ((e = (x)) != cudaSuccess) { ret = ctx->cuda_fail(e, #x); break; }
         TRY(d_out.ensure((size_t)grid * block));
-        TRY(wrt::launch_fp64_peak(d_out.p, grid, block, 1u << 10, ctx->stream));  // warm-up
+        TRY(launch(d_out.p, grid, block, 1u << 10, ctx->stream));  // warm-up
         double best = 0.0;
         for (int rep = 0; rep < 5; ++rep) {
             TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-            TRY(wrt::launch_fp64_peak(d_out.p, grid, block, iters, ctx->stream));
+            TRY(launch(d_out.p, grid, block, iters, ctx->stream));
             TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
             TRY(cudaStreamSynchronize(ctx->stream));
             float ms = 0;
@@ -755,6 +771,8 @@ extern "C" int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second) {
     d_out.release();
     return ret;
 }
+extern "C" int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second) { return issue_peak(ctx, fma_per_second, false); }
+extern "C" int wrt_fp32_issue_peak(wrt_ctx* ctx, double* fma_per_second) { return issue_peak(ctx, fma_per_second, true); }
 
 extern "C" int wrt_get_stats(const wrt_ctx* ctx, wrt_stats* out) {
     if (!ctx || !out) return WRT_E_INVALID;

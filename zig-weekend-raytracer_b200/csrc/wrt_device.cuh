@@ -115,6 +115,9 @@ struct SobolTables {               // live part of sobolmatrices.zig for one res
     uint32_t log2_scale, scale;
     uint32_t b_bytes, _pad;        // bytes of b = (px << m | py) ^ delta that can be non-zero
     const SobolLut* lut;
+    // Sample s -> s + 1 of one pixel: index and sample bits are GF(2)-linear in (s, pixel), and s ^ (s + 1) = 2^(k+1) - 1
+    // with k = number of trailing ones of s, so the bits of dims 0/1 advance by one XOR with inc[k] (built at upload).
+    uint32_t inc0[32], inc1[32];
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -227,14 +230,32 @@ __device__ __forceinline__ float sobol_sample_bits_to_float(uint32_t v) {
     float vf = __uint2float_rn(v);                       // @floatFromInt, round to nearest even
     return fminf(__fmul_rn(vf, 0x1p-32f), 0x1.fffffep-1f);  // sampler.zig:262-263
 }
-__device__ __forceinline__ void sobol_pixel_2d(const SobolTables& T, uint64_t index, uint32_t px, uint32_t py, double& ox, double& oy) {
+// the sample bits of dimensions 0 and 1 for a Sobol index (sobolSample with the noop randomiser, before the float conversion)
+__device__ __forceinline__ void sobol_pixel_bits(const SobolTables& T, uint64_t index, uint32_t& v0, uint32_t& v1) {
     // dimension 0 is the van der Corput sequence: its matrix is the bit reversal of the low 32 index bits
     // (SobolMatrices32[i] = 0x80000000 >> i for i < 32, 0 above; checked when the tables are loaded)
-    const uint32_t v0 = __brev((uint32_t)index);
+    v0 = __brev((uint32_t)index);
     const SobolLut* __restrict__ L = T.lut;
-    uint32_t v1 = 0;
+    v1 = 0;
 #pragma unroll
     for (int k = 0; k < 7; ++k) v1 ^= __ldg(&L->dim1[k][(index >> (8 * k)) & 255u]);
+}
+// advance the bits from sample s_prev to s_prev + 1 of the same pixel
+__device__ __forceinline__ void sobol_pixel_bits_next(const SobolTables& T, uint32_t s_prev, uint32_t& v0, uint32_t& v1) {
+    const int k = __ffs(~s_prev) - 1;  // trailing ones of s_prev
+    v0 ^= T.inc0[k & 31];
+    v1 ^= T.inc1[k & 31];
+}
+__device__ __forceinline__ void sobol_bits_to_offsets(const SobolTables& T, uint32_t v0, uint32_t v1, uint32_t px, uint32_t py, double& ox, double& oy) {
+    const double one_minus_eps = (double)0x1.fffffep-1f;
+    double rx = (double)sobol_sample_bits_to_float(v0) * (double)T.scale - (double)px;
+    double ry = (double)sobol_sample_bits_to_float(v1) * (double)T.scale - (double)py;
+    ox = fmax(0.0, fmin(rx, one_minus_eps));  // std.math.clamp, sampler.zig:229-231
+    oy = fmax(0.0, fmin(ry, one_minus_eps));
+}
+__device__ __forceinline__ void sobol_pixel_2d(const SobolTables& T, uint64_t index, uint32_t px, uint32_t py, double& ox, double& oy) {
+    uint32_t v0, v1;
+    sobol_pixel_bits(T, index, v0, v1);
     const double one_minus_eps = (double)0x1.fffffep-1f;
     double rx = (double)sobol_sample_bits_to_float(v0) * (double)T.scale - (double)px;
     double ry = (double)sobol_sample_bits_to_float(v1) * (double)T.scale - (double)py;

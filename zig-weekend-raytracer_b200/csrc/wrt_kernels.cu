@@ -32,11 +32,35 @@ __device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2])
 
 // sampleRay, render.zig:144-174 (+ sampleDefocusDisk :182-185, rng.sampleUnitDiskXY rng.zig:76-78).
 // rng == nullptr: gate-1 dump (pinhole, time 0).  Draws: block 0 = (lens radius, lens angle), block 1.lo = time.
+__device__ __forceinline__ Ray sample_ray_at(const RenderConstants& rc, uint32_t col, uint32_t row, double ox, double oy, bool dof,
+                                             bool need_time, const Rng* rng);
 __device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, bool dof, bool need_time,
                                           const Rng* rng) {
     uint64_t idx = sobol_interval_to_index(c_sobol, s, col, row);
     double ox, oy;
     sobol_pixel_2d(c_sobol, idx, col, row, ox, oy);
+    return sample_ray_at(rc, col, row, ox, oy, dof, need_time, rng);
+}
+// The same for a lane that walks the samples of one pixel in order: the Sobol bits of sample s are those of s - 1 advanced
+// by one XOR (SobolTables::inc*), only the first sample of a job pays for the index inversion.  Bit-identical jitter.
+struct PixelSobol {
+    uint32_t v0, v1;
+    bool primed;
+};
+__device__ __forceinline__ Ray sample_ray_seq(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, PixelSobol& ps, bool dof,
+                                              bool need_time, const Rng* rng) {
+    if (ps.primed) {
+        sobol_pixel_bits_next(c_sobol, s - 1u, ps.v0, ps.v1);
+    } else {
+        sobol_pixel_bits(c_sobol, sobol_interval_to_index(c_sobol, s, col, row), ps.v0, ps.v1);
+        ps.primed = true;
+    }
+    double ox, oy;
+    sobol_bits_to_offsets(c_sobol, ps.v0, ps.v1, col, row, ox, oy);
+    return sample_ray_at(rc, col, row, ox, oy, dof, need_time, rng);
+}
+__device__ __forceinline__ Ray sample_ray_at(const RenderConstants& rc, uint32_t col, uint32_t row, double ox, double oy, bool dof,
+                                             bool need_time, const Rng* rng) {
     d3 sample = (ld3(rc.cam.pixel00_loc) + ld3(rc.cam.pixel_delta_u) * ((double)col + ox)) +
                 ld3(rc.cam.pixel_delta_v) * ((double)row + oy);
     d3 origin = ld3(rc.cam.position);
@@ -293,6 +317,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             }
             if (!alive && have_job) {
                 rng.sample = s;
+                                // (the incremental Sobol form of the lane kernel below costs this kernel 2 %: two more live registers at its 80-register cap)
                 ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
                 beta = mk(1, 1, 1); L = mk(0, 0, 0);
                 depth_left = rc.max_depth;
@@ -348,11 +373,13 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
             rng.pixel = row * rc.width + col;
             rng.sample = 0;
+            PixelSobol sob;
+            sob.v0 = 0; sob.v1 = 0; sob.primed = false;
 
             for (;;) {
                 if (!alive && lane_active && s < s_last) {
                     rng.sample = s;
-                    ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
+                    ray = sample_ray_seq(rc, col, row, s, sob, dof, need_time, &rng);
                     beta = mk(1, 1, 1); L = mk(0, 0, 0);
                     depth_left = rc.max_depth;
                     alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
@@ -794,6 +821,20 @@ __global__ void fp64_peak_kernel(double* out, uint32_t iters, double seed) {
 }
 cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream) {
     fp64_peak_kernel<<<grid, block, 0, stream>>>(out, iters, 0.5);
+    return cudaGetLastError();
+}
+// the same probe on the binary32 pipe (the culler's arithmetic)
+__global__ void fp32_peak_kernel(double* out, uint32_t iters, float seed) {
+    float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const float m = 1.0000001f, c = 1e-9f;
+    for (uint32_t i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = (double)(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+}
+cudaError_t launch_fp32_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream) {
+    fp32_peak_kernel<<<grid, block, 0, stream>>>(out, iters, 0.5f);
     return cudaGetLastError();
 }
 

@@ -88,5 +88,6 @@ cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const
 cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
                                    uint32_t owen_fast, uint32_t seed, float* out, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream);
+cudaError_t launch_fp32_peak(double* out, uint32_t grid, uint32_t block, uint32_t iters, cudaStream_t stream);
 
 }  // namespace wrt
