@@ -276,12 +276,14 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
         unsigned long long job = 0;     // this lane's job
         bool have_job = false, drained = false;
         uint32_t col = 0, row = 0, s = 0, s_last = 0;
-        d3 color = mk(0, 0, 0);
+        // Few values live across the traversal (the kernel runs at an 80-register cap): the job's colour sum sits in its
+        // accumulator slot and is updated once per path, the radiance of a path exists only in the iteration that ends it
+        // (only terminal events add radiance: emission, background, the depth cut).
         bool alive = false;
         uint32_t depth_left = 0;
         Ray ray;
         ray.o = mk(0, 0, 0); ray.d = mk(0, 0, 1); ray.time = 0.0;
-        d3 beta = mk(1, 1, 1), L = mk(0, 0, 0);
+        d3 beta = mk(1, 1, 1);
 
         for (;;) {
             const bool want = !have_job && !drained;
@@ -301,12 +303,11 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                         row = rc.row_shard_index + local_row * rc.row_shard_count;
                         s = rc.sample_begin + chunk * rc.chunk_size;
                         s_last = min(s + rc.chunk_size, rc.sample_end);
-                        color = mk(0, 0, 0);
                         rng.pixel = row * rc.width + col;
                         have_job = true;
+                        double* slot = accum + job * 3ull;
+                        slot[0] = 0.0; slot[1] = 0.0; slot[2] = 0.0;
                         if (rc.max_depth == 0) {  // depth 0 returns black for every sample (render.zig:199)
-                            double* slot = accum + job * 3ull;
-                            slot[0] = 0.0; slot[1] = 0.0; slot[2] = 0.0;
                             n_paths += s_last - s;
                             have_job = false;
                         }
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 rng.sample = s;
                                 // (the incremental Sobol form of the lane kernel below costs this kernel 2 %: two more live registers at its 80-register cap)
                 ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
-                beta = mk(1, 1, 1); L = mk(0, 0, 0);
+                beta = mk(1, 1, 1);
                 depth_left = rc.max_depth;
                 alive = true;
                 ++n_paths;
@@ -331,17 +332,17 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             const ClosestHit ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
             if (alive) {
                 ++n_rays;
+                d3 L = mk(0, 0, 0);
                 const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
                 --depth_left;
                 if (!cont || depth_left == 0) {
                     if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
-                    color = color + L * scale;     // render.zig:129-135
+                    double* slot = accum + job * 3ull;  // (chunk, pixel) slot == job index
+                    slot[0] = slot[0] + L.x * scale;    // color += L * scale, render.zig:129-135
+                    slot[1] = slot[1] + L.y * scale;
+                    slot[2] = slot[2] + L.z * scale;
                     alive = false;
-                    if (++s == s_last) {           // chunk complete: its sum goes to the (chunk, pixel) slot == job index
-                        double* slot = accum + job * 3ull;
-                        slot[0] = color.x; slot[1] = color.y; slot[2] = color.z;
-                        have_job = false;
-                    }
+                    if (++s == s_last) have_job = false;  // chunk complete
                 }
             }
         }
