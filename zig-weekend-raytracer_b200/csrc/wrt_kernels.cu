@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
         unsigned long long job = 0;     // this lane's job
         bool have_job = false, drained = false;
         uint32_t col = 0, row = 0, s = 0, s_last = 0;
+        uint32_t acc_rays = 0, acc_paths = 0;  // 32-bit tallies, flushed to the 64-bit counters every ~64 K rays and at the end
         // Few values live across the traversal (the kernel runs at an 80-register cap): the job's colour sum sits in its
         // accumulator slot and is updated once per path, the radiance of a path exists only in the iteration that ends it
         // (only terminal events add radiance: emission, background, the depth cut).
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                         double* slot = accum + job * 3ull;
                         slot[0] = 0.0; slot[1] = 0.0; slot[2] = 0.0;
                         if (rc.max_depth == 0) {  // depth 0 returns black for every sample (render.zig:199)
-                            n_paths += s_last - s;
+                            atomicAdd(&counters[2], (unsigned long long)(s_last - s));
                             have_job = false;
                         }
                     } else {
@@ -323,7 +324,6 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 beta = mk(1, 1, 1);
                 depth_left = rc.max_depth;
                 alive = true;
-                ++n_paths;
             }
             if (!__any_sync(0xffffffffu, alive)) {
                 if (__all_sync(0xffffffffu, drained)) break;  // no lane has a job left and the queue is empty
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             }
             const ClosestHit ch = closest_hit_packet<CULL>(S, alive, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
             if (alive) {
-                ++n_rays;
+                ++acc_rays;
                 d3 L = mk(0, 0, 0);
                 const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
                 --depth_left;
@@ -342,10 +342,17 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                     slot[1] = slot[1] + L.y * scale;
                     slot[2] = slot[2] + L.z * scale;
                     alive = false;
+                    ++acc_paths;
                     if (++s == s_last) have_job = false;  // chunk complete
+                    if (acc_rays >= (1u << 16)) {
+                        atomicAdd(&counters[1], (unsigned long long)acc_rays);
+                        atomicAdd(&counters[2], (unsigned long long)acc_paths);
+                        acc_rays = 0; acc_paths = 0;
+                    }
                 }
             }
         }
+        n_rays = acc_rays; n_paths = acc_paths;  // the remainder joins the warp reduction below
     } else {
         // Per-lane scan: warp jobs (row, 32-column block, sample chunk) keep the lanes of a warp on neighbouring pixels, whose
         // traversals are of similar length; lanes still regenerate their own samples inside the job.
