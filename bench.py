@@ -41,8 +41,8 @@ WORKLOADS = {
     "C2": dict(name="cornell_box 1024x1024, 10000 spp, depth 50 (light importance sampling, pdf.zig mixture)", scene="cornell_box",
                width=1024, height=1024, spp=10000, depth=50, b_ray=332, f_ray=354,
                # dram__bytes_read.sum + dram__bytes_write.sum of render_kernel / rays of that launch, from the ncu --set full
-               # capture of this workload at 512 spp (profiles/r01_ncu_render_kernel_packet_summary.txt): 3.05 GB / 2.64e9 rays
-               dram_b_per_ray_ncu=1.155),
+               # capture of this workload at 64 spp (profiles/r01_ncu_render_kernel_packet_summary.txt): 471.5 MB / 3.38e8 rays
+               dram_b_per_ray_ncu=1.395),
     "C3": dict(name="balls (book-1 final, ~484 spheres through BVH) 1920x1080, 512 spp, depth 50", scene="balls", width=1920,
                height=1080, spp=512, depth=50, b_ray=572, f_ray=658),
     "C4": dict(name="earth (image-textured sphere + diffuse lights) 1920x1080, 1024 spp, depth 20", scene="earth", width=1920,
@@ -363,7 +363,7 @@ def main():
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": (wl["dram_b_per_ray_ncu"] * rays_all / args.steps) if "dram_b_per_ray_ncu" in wl else None,
-                     "traffic_unit": "bytes per launch (ncu DRAM bytes per ray at 512 spp x rays of this launch)",
+                     "traffic_unit": "bytes per launch (ncu DRAM bytes per ray at 64 spp x rays of this launch)",
                      "algorithmic_bytes_per_launch": wl["b_ray"] * rays_all / args.steps,
                      "kernel": "render_kernel", "kernel_ms_per_launch": kern_ms_max / args.steps,
                      "algorithmic_bytes_per_ray": wl["b_ray"], "peak_source": peak_src,
