@@ -256,6 +256,15 @@ WRT_API int wrt_render_device(wrt_ctx* ctx, const wrt_camera* cam, const wrt_par
 WRT_API int wrt_encode_rgb8(wrt_ctx* ctx, uint8_t* rgb_out);
 
 /* Gates / diagnostics ------------------------------------------------------------------------- */
+/* The PPM writer's body on the device (writer/writer.zig:16-123): formats an RGB8 frame as the reference's file image —
+ * "P3\n{W} {H}\n255\n" followed by one "{r} {g} {b}\n" line per pixel, packed — into `out`.  rgb8 == NULL formats the
+ * frame of the last wrt_render* call (quantised on the device by the resolve pass; width x height must be that frame);
+ * otherwise width*height*3 host bytes are uploaded first (e.g. a frame gathered from several GPUs).  `capacity` must be
+ * at least header + 12 bytes per pixel, the size the reference gives its file (writer.zig:20); the bytes between
+ * *content_bytes and that size are zeroed, as in the reference's mmap'ed file.  `out` may be the mapping itself. */
+WRT_API int wrt_format_ppm(wrt_ctx* ctx, const uint8_t* rgb8, uint32_t width, uint32_t height, uint8_t* out, uint64_t capacity,
+                   uint64_t* content_bytes);
+
 /* Gate 1: closest hit of the PRIMARY ray of samples [0, n_samples) of every pixel (row-major, sample
  * innermost): primitive id (WRT_NONE = miss) and t.  Depth of field is disabled. */
 WRT_API int wrt_primary_hits(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, uint32_t n_samples,

@@ -499,6 +499,42 @@ def test_host_mirror_scene_draw_end_to_end(wrt, wro, images):
     hs.close(); sc.close()
 
 
+def test_device_ppm_formatter_writes_the_reference_file(ctx, wrt, wro, tmp_path):
+    """wrt_format_ppm (the writer's body on the device) produces byte for byte the file the reference's writer produces —
+    header, packed "{r} {g} {b}\\n" lines, NUL tail — for the frame of the last render and for an uploaded RGB8 frame,
+    including ragged sizes (not a multiple of the 1024-pixel block) and every digit-count combination."""
+    import importlib
+    host = importlib.import_module("zig-weekend-raytracer_b200.host")
+    sc = wro.OracleScene("cornell_box")
+    ctx.upload_scene(sc.flatten())
+    for w, h in ((61, 37), (128, 64), (1, 1)):
+        fb = ctx.render(sc.camera(w, h), sc.params(w, h, 4, 8, seed=3))
+        got, n = ctx.format_ppm(w, h)
+        ref = tmp_path / f"ref_{w}x{h}.ppm"
+        n_ref = host.write_ppm(str(ref), fb, threads=3)  # the host mirror of writer.zig (checked against the oracle elsewhere)
+        want = np.frombuffer(ref.read_bytes(), np.uint8)
+        assert n == n_ref
+        np.testing.assert_array_equal(got, want)
+        assert not got[n:].any() and got[n - 1] == ord("\n")
+    # an uploaded frame with all byte values: every 1/2/3-digit combination and block boundaries
+    rng = np.random.default_rng(5)
+    w, h = 257, 129
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    rgb[0, :256, 0] = np.arange(256); rgb[1, :256, 1] = np.arange(256); rgb[2, :256, 2] = np.arange(256)
+    got, n = ctx.format_ppm(w, h, rgb)
+    ref = tmp_path / "ref_rgb.ppm"
+    n_ref = host.write_ppm_rgb8(str(ref), rgb, threads=2)
+    assert n == n_ref
+    np.testing.assert_array_equal(got, np.frombuffer(ref.read_bytes(), np.uint8))
+    text = bytes(got[:n]).decode().split("\n")
+    assert text[0] == "P3" and text[1] == f"{w} {h}" and text[2] == "255"
+    vals = np.array([list(map(int, line.split())) for line in text[3:-1]], dtype=np.uint8)
+    np.testing.assert_array_equal(vals.reshape(h, w, 3), rgb)
+    with pytest.raises(wrt.WrtError):
+        ctx.format_ppm(w + 1, h)  # not the last rendered frame
+    sc.close()
+
+
 def test_cli_renders_a_ppm(wrt, wro, tmp_path):
     """`weekend-raytracer` with the reference's flags (README.md:36) writes the PPM the reference writer would write for
     the same frame."""
@@ -514,6 +550,12 @@ def test_cli_renders_a_ppm(wrt, wro, tmp_path):
         assert msg in r.stderr
     raw = out.read_bytes()
     assert raw.startswith(b"P3\n40 30\n255\n") and len(raw) == 40 * 30 * 12 + len(b"P3\n40 30\n255\n")
+    out_dev = tmp_path / "image_dev.ppm"
+    r2 = subprocess.run([str(host.CLI_PATH), "--image_width=40", "--image_height=30", "--ray_bounce_max_depth=10",
+                         "--thread_pool_size=4", "--samples_per_pixel=8", f"--image_out_path={out_dev}", "--seed=1", "--writer=device"],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert out_dev.read_bytes() == raw  # the device formatter writes the same file
     sc = wro.OracleScene("emissive")  # the default scene (main.zig:25)
     want, _ = sc.render(sc.camera(40, 30), sc.params(40, 30, 8, 10, seed=1), wro.RNG_COUNTER)
     rgb = wro.encode_image(want)

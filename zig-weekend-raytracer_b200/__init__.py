@@ -25,7 +25,7 @@ from .abi import Camera, Params, Scene, Stats
 ABI_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_upload_scene", "wrt_render",
     "wrt_render_device", "wrt_encode_rgb8", "wrt_primary_hits", "wrt_trace_rays", "wrt_sobol_pixel_samples",
-    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak",
+    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm",
 ]
 
 
@@ -60,6 +60,7 @@ def _load() -> C.CDLL:
     lib.wrt_get_stats.argtypes = [vp, vp]
     lib.wrt_fp64_issue_peak.argtypes = [vp, vp]
     lib.wrt_fp32_issue_peak.argtypes = [vp, vp]
+    lib.wrt_format_ppm.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     for name in ABI_SYMBOLS:
         if name not in ("wrt_destroy", "wrt_last_error", "wrt_abi_version"):
             getattr(lib, name).restype = C.c_int
@@ -118,6 +119,20 @@ class Context:
         out = C.c_double()
         self._check(lib.wrt_fp64_issue_peak(self._h, C.byref(out)))
         return out.value
+
+    def format_ppm(self, width: int, height: int, rgb8: np.ndarray | None = None) -> tuple[np.ndarray, int]:
+        """The reference's PPM file image (header + packed pixel lines + NUL tail) of the last rendered frame, or of
+        `rgb8` (H x W x 3 uint8), formatted on the device.  Returns (file bytes, content length)."""
+        header = f"P3\n{width} {height}\n255\n".encode()
+        out = np.zeros(len(header) + 12 * width * height, np.uint8)
+        n = C.c_uint64()
+        src = None
+        if rgb8 is not None:
+            rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+            assert rgb8.size == width * height * 3
+            src = _ptr(rgb8)
+        self._check(lib.wrt_format_ppm(self._h, src, width, height, _ptr(out), out.size, C.byref(n)))
+        return out, int(n.value)
 
     def fp32_issue_peak(self) -> float:
         """Measured binary32 FMA issue rate of the device, thread-level FMAs per second."""

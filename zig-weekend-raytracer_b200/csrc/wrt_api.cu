@@ -88,6 +88,9 @@ struct wrt_ctx {
     wrt::DeviceScene ds_pruned{};  // ds with the pruned program (packet scan, WRT_CULL_TIGHT); == ds when nothing was dropped
     DevBuf<uint4> d_ops;
     DevBuf<uint4> d_ops_pruned;
+    DevBuf<uint8_t> d_ppm_in, d_ppm_body;
+    DevBuf<uint32_t> d_ppm_blocks;
+    DevBuf<unsigned long long> d_ppm_offsets;
     DevBuf<wrt::BoxRef> d_boxes_ref;
     DevBuf<wrt::BoxTight> d_boxes_tight;
     DevBuf<wrt::Node2> d_nodes2;
@@ -201,6 +204,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
+    ctx->d_ppm_in.release(); ctx->d_ppm_body.release(); ctx->d_ppm_blocks.release(); ctx->d_ppm_offsets.release();
     ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_counters.release();
     if (ctx->h_wf_counters) cudaFreeHost(ctx->h_wf_counters);
     for (auto& ev : ctx->ev)
@@ -590,6 +594,46 @@ extern "C" int wrt_encode_rgb8(wrt_ctx* ctx, uint8_t* rgb_out) {
     // the resolve pass already quantised the frame (fused final pass); just fetch it
     CU(cudaMemcpyAsync(rgb_out, ctx->d_rgb8.p, (size_t)ctx->last_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return WRT_OK;
+}
+
+extern "C" int wrt_format_ppm(wrt_ctx* ctx, const uint8_t* rgb8, uint32_t width, uint32_t height, uint8_t* out, uint64_t capacity,
+                              uint64_t* content_bytes) {
+    if (!ctx) return WRT_E_INVALID;
+    int rc_ = bind_device(ctx);
+    if (rc_) return rc_;
+    if (!out || !content_bytes) return ctx->fail(WRT_E_INVALID, "wrt_format_ppm: out / content_bytes is NULL");
+    if (width == 0 || height == 0) return ctx->fail(WRT_E_INVALID, "image dimensions must be non-zero");
+    const uint64_t n64 = (uint64_t)width * height;
+    if (n64 > 0xFFFFFFFFull) return ctx->fail(WRT_E_LIMIT, "more than 2^32 pixels");
+    const uint32_t n_pixels = (uint32_t)n64;
+    if (!rgb8) {
+        if (!ctx->last_valid) return ctx->fail(WRT_E_STATE, "wrt_format_ppm: no frame rendered yet");
+        if (ctx->last_pixels != n_pixels) return ctx->fail(WRT_E_INVALID, "wrt_format_ppm: width x height is not the last rendered frame");
+    }
+    char header[64];
+    const int header_len = std::snprintf(header, sizeof header, "P3\n%u %u\n255\n", width, height);  // writer.zig:9,18
+    const uint64_t file_size = (uint64_t)header_len + 12ull * n64;                                     // writer.zig:20
+    if (capacity < file_size) return ctx->fail(WRT_E_INVALID, "wrt_format_ppm: capacity < header + 12 bytes per pixel");
+    const uint32_t n_blocks = wrt::ppm_block_count(n_pixels);
+    const uint8_t* d_rgb = ctx->d_rgb8.p;
+    if (rgb8) {
+        CU(ctx->d_ppm_in.ensure((size_t)n64 * 3));
+        CU(cudaMemcpyAsync(ctx->d_ppm_in.p, rgb8, (size_t)n64 * 3, cudaMemcpyHostToDevice, ctx->stream));
+        d_rgb = ctx->d_ppm_in.p;
+    }
+    CU(ctx->d_ppm_body.ensure((size_t)n64 * 12));
+    CU(ctx->d_ppm_blocks.ensure(n_blocks));
+    CU(ctx->d_ppm_offsets.ensure((size_t)n_blocks + 1));
+    CU(wrt::launch_format_ppm(d_rgb, n_pixels, ctx->d_ppm_blocks.p, ctx->d_ppm_offsets.p, ctx->d_ppm_body.p, ctx->stream));
+    unsigned long long body = 0;
+    CU(cudaMemcpyAsync(&body, ctx->d_ppm_offsets.p + n_blocks, sizeof body, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, header, (size_t)header_len);
+    CU(cudaMemcpyAsync(out + header_len, ctx->d_ppm_body.p, (size_t)body, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::memset(out + header_len + body, 0, (size_t)(file_size - header_len - body));  // the NUL tail of the reference's mmap'ed file
+    *content_bytes = (uint64_t)header_len + body;
     return WRT_OK;
 }
 

@@ -747,6 +747,116 @@ __global__ void encode_kernel(const double* __restrict__ fb, uint32_t stride_dou
     rgb8[3 * (size_t)i + 2] = encode_channel(px[2]);
 }
 
+// ---- PPM body on the device (writer.zig:16-123) ------------------------------------------------------------------
+// The reference sizes every 1024-pixel chunk of "{r} {g} {b}\n" lines in a serial pre-pass on the main thread and then
+// formats the chunks on its thread pool (writer.zig:33-66).  Here: per-block byte counts, one exclusive scan, then every
+// block formats its 1024 pixels into shared memory and copies them to their final file offset with coalesced stores.
+#define WRT_PPM_BLOCK 256
+#define WRT_PPM_PIXELS_PER_THREAD 4
+#define WRT_PPM_BLOCK_PIXELS (WRT_PPM_BLOCK * WRT_PPM_PIXELS_PER_THREAD)
+__device__ __forceinline__ uint32_t ppm_digits(uint32_t v) { return v > 99u ? 3u : (v > 9u ? 2u : 1u); }  // sizeOfDigit, writer.zig:107-114
+__device__ __forceinline__ uint32_t ppm_line_bytes(const uint8_t* px) {  // sizeOfLine, writer.zig:96-100
+    return 3u + ppm_digits(px[0]) + ppm_digits(px[1]) + ppm_digits(px[2]);
+}
+__device__ __forceinline__ uint32_t ppm_thread_bytes(const uint8_t* __restrict__ rgb, uint32_t first, uint32_t n_pixels, uint32_t len[WRT_PPM_PIXELS_PER_THREAD]) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < WRT_PPM_PIXELS_PER_THREAD; ++k) {
+        const uint32_t i = first + k;
+        len[k] = (i < n_pixels) ? ppm_line_bytes(rgb + 3 * (size_t)i) : 0u;
+        sum += len[k];
+    }
+    return sum;
+}
+// exclusive prefix of `v` over the block (256 threads); `total` = block sum
+__device__ __forceinline__ uint32_t ppm_block_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= (uint32_t)off) inc += up;
+    }
+    if (lane == 31u) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < WRT_PPM_BLOCK / 32; ++w) {
+        const uint32_t ws = warp_sums[w];
+        if (w < warp) base += ws;
+        total += ws;
+    }
+    __syncthreads();
+    return base + inc - v;
+}
+__global__ void __launch_bounds__(WRT_PPM_BLOCK) ppm_block_bytes_kernel(const uint8_t* __restrict__ rgb, uint32_t n_pixels, uint32_t* __restrict__ block_bytes) {
+    __shared__ uint32_t warp_sums[WRT_PPM_BLOCK / 32];
+    uint32_t len[WRT_PPM_PIXELS_PER_THREAD];
+    const uint32_t first = blockIdx.x * WRT_PPM_BLOCK_PIXELS + threadIdx.x * WRT_PPM_PIXELS_PER_THREAD;
+    uint32_t total;
+    ppm_block_scan(ppm_thread_bytes(rgb, first, n_pixels, len), warp_sums, total);
+    if (threadIdx.x == 0) block_bytes[blockIdx.x] = total;
+}
+// one block: exclusive scan of the block byte counts into 64-bit file offsets; offsets[n_blocks] = body size
+__global__ void __launch_bounds__(1024) ppm_scan_kernel(const uint32_t* __restrict__ block_bytes, uint32_t n_blocks, unsigned long long* __restrict__ offsets) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n_blocks + 1023u) / 1024u;
+    const uint32_t lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += block_bytes[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const unsigned long long v = part[t]; part[t] = run; run += v; }
+        offsets[n_blocks] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; ++i) { offsets[i] = run; run += block_bytes[i]; }
+}
+__device__ __forceinline__ uint32_t ppm_put(uint8_t* out, uint32_t v, uint8_t sep) {  // "{d}" + separator, writer.zig:62
+    uint32_t n = 0;
+    if (v > 99u) out[n++] = (uint8_t)('0' + v / 100u);
+    if (v > 9u) out[n++] = (uint8_t)('0' + (v / 10u) % 10u);
+    out[n++] = (uint8_t)('0' + v % 10u);
+    out[n++] = sep;
+    return n;
+}
+__global__ void __launch_bounds__(WRT_PPM_BLOCK) ppm_format_kernel(const uint8_t* __restrict__ rgb, uint32_t n_pixels,
+                                                                   const unsigned long long* __restrict__ offsets, uint8_t* __restrict__ body) {
+    __shared__ uint32_t warp_sums[WRT_PPM_BLOCK / 32];
+    __shared__ uint8_t text[WRT_PPM_BLOCK_PIXELS * 12];
+    uint32_t len[WRT_PPM_PIXELS_PER_THREAD];
+    const uint32_t first = blockIdx.x * WRT_PPM_BLOCK_PIXELS + threadIdx.x * WRT_PPM_PIXELS_PER_THREAD;
+    uint32_t total;
+    uint32_t at = ppm_block_scan(ppm_thread_bytes(rgb, first, n_pixels, len), warp_sums, total);
+#pragma unroll
+    for (int k = 0; k < WRT_PPM_PIXELS_PER_THREAD; ++k) {
+        const uint32_t i = first + k;
+        if (i < n_pixels) {
+            const uint8_t* px = rgb + 3 * (size_t)i;
+            at += ppm_put(text + at, px[0], ' ');
+            at += ppm_put(text + at, px[1], ' ');
+            at += ppm_put(text + at, px[2], '\n');
+        }
+    }
+    __syncthreads();
+    uint8_t* dst = body + offsets[blockIdx.x];
+    for (uint32_t b = threadIdx.x; b < total; b += WRT_PPM_BLOCK) dst[b] = text[b];
+}
+cudaError_t launch_format_ppm(const uint8_t* rgb, uint32_t n_pixels, uint32_t* block_bytes, unsigned long long* offsets, uint8_t* body,
+                              cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    const uint32_t n_blocks = (n_pixels + WRT_PPM_BLOCK_PIXELS - 1) / WRT_PPM_BLOCK_PIXELS;
+    ppm_block_bytes_kernel<<<n_blocks, WRT_PPM_BLOCK, 0, stream>>>(rgb, n_pixels, block_bytes);
+    ppm_scan_kernel<<<1, 1024, 0, stream>>>(block_bytes, n_blocks, offsets);
+    ppm_format_kernel<<<n_blocks, WRT_PPM_BLOCK, 0, stream>>>(rgb, n_pixels, offsets, body);
+    return cudaGetLastError();
+}
+uint32_t ppm_block_count(uint32_t n_pixels) { return (n_pixels + WRT_PPM_BLOCK_PIXELS - 1) / WRT_PPM_BLOCK_PIXELS; }
+
 template <int CULL>
 __global__ void primary_hits_kernel(DeviceScene S, uint32_t n_samples, uint32_t* __restrict__ ids, double* __restrict__ ts) {
     const RenderConstants& rc = c_rc;

@@ -78,6 +78,10 @@ cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool pack
 cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
                            uint32_t stride_doubles, uint8_t* rgb8, cudaStream_t stream);
 cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_pixels, uint8_t* rgb8, cudaStream_t stream);
+// PPM body of an RGB8 frame (writer.zig): per-block byte counts -> offsets[n_blocks + 1] (last = body size) -> text
+cudaError_t launch_format_ppm(const uint8_t* rgb, uint32_t n_pixels, uint32_t* block_bytes, unsigned long long* offsets, uint8_t* body,
+                              cudaStream_t stream);
+uint32_t ppm_block_count(uint32_t n_pixels);
 cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
                                 cudaStream_t stream);
 cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool packet, const double* origins, const double* dirs, uint64_t n,

@@ -46,6 +46,7 @@ struct UserArgs {  // main.zig:20-28 (+ additions)
     uint32_t cull = WRT_CULL_TIGHT;
     std::string asset_dir = "assets/";
     uint32_t synthetic_prims = 1u << 20;
+    bool writer_on_device = false;  // --writer=device: wrt_format_ppm instead of the host thread pool
 };
 
 void printUsage(FILE* out) {  // argparser.zig:94-113
@@ -54,7 +55,7 @@ void printUsage(FILE* out) {  // argparser.zig:94-113
     std::fprintf(out, "\t--thread_pool_size=<usize>\n\t--scene=<scene.SceneType>\n");
     for (const auto& n : wrh::sceneTypeNames()) std::fprintf(out, "\t\t%s\n", n.c_str());
     std::fprintf(out, "\t--samples_per_pixel=<usize>\n\t--ray_bounce_max_depth=<usize>\n");
-    std::fprintf(out, "\t--device=<i32>\n\t--seed=<u64>\n\t--cull=<tight|reference>\n\t--asset_dir=<[]const u8>\n\t--synthetic_prims=<u32>\n");
+    std::fprintf(out, "\t--device=<i32>\n\t--seed=<u64>\n\t--cull=<tight|reference>\n\t--asset_dir=<[]const u8>\n\t--synthetic_prims=<u32>\n\t--writer=<host|device>\n");
 }
 
 bool parseUnsigned(const std::string& v, unsigned long long& out) {  // std.fmt.parseInt(.., 10)
@@ -75,7 +76,7 @@ bool parseUnsigned(const std::string& v, unsigned long long& out) {  // std.fmt.
 // cacheArgVal + parse (argparser.zig:64-136): any number of leading '-', key=value, help / h, unknown keys rejected.
 UserArgs parseUserArgs(int argc, char** argv) {
     static const char* known[] = {"image_width", "image_height", "image_out_path", "thread_pool_size", "scene", "samples_per_pixel",
-                                  "ray_bounce_max_depth", "device", "seed", "cull", "asset_dir", "synthetic_prims"};
+                                  "ray_bounce_max_depth", "device", "seed", "cull", "asset_dir", "synthetic_prims", "writer"};
     std::map<std::string, std::string> cache;
     for (int a = 1; a < argc; ++a) {
         std::string arg = argv[a];
@@ -115,6 +116,11 @@ UserArgs parseUserArgs(int argc, char** argv) {
     tmp = 1; get_size("seed", tmp, false); args.seed = tmp;
     tmp = args.synthetic_prims; get_size("synthetic_prims", tmp, false); args.synthetic_prims = static_cast<uint32_t>(tmp);
     if (cache.count("asset_dir")) args.asset_dir = cache["asset_dir"];
+    if (cache.count("writer")) {
+        if (cache["writer"] == "device") args.writer_on_device = true;
+        else if (cache["writer"] == "host") args.writer_on_device = false;
+        else throw ParseArgsError::ParseEnumFailed;
+    }
     if (cache.count("cull")) {
         if (cache["cull"] == "tight") args.cull = WRT_CULL_TIGHT;
         else if (cache["cull"] == "reference") args.cull = WRT_CULL_REFERENCE;
@@ -182,7 +188,8 @@ int main(int argc, char** argv) {
 
         wrh::WriterPPM writer;  // main.zig:100-104
         writer.thread_pool = &thread_pool;
-        writer.write(args.image_out_path, framebuffer.buffer.data(), wrh::Framebuffer::kLanes, framebuffer.num_cols, framebuffer.num_rows);
+        if (args.writer_on_device) writer.writeOnDevice(backend.ctx(), args.image_out_path, nullptr, framebuffer.num_cols, framebuffer.num_rows);
+        else writer.write(args.image_out_path, framebuffer.buffer.data(), wrh::Framebuffer::kLanes, framebuffer.num_cols, framebuffer.num_rows);
         timer.logInfoElapsed("scene written to file");
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

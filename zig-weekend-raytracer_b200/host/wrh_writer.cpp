@@ -177,4 +177,16 @@ size_t WriterPPM::writeQuantised(const std::string& out_path, const uint8_t* rgb
     });
 }
 
+size_t WriterPPM::writeOnDevice(wrt_ctx* ctx, const std::string& out_path, const uint8_t* rgb, size_t num_cols, size_t num_rows) const {
+    char header[64];
+    const int header_len = std::snprintf(header, sizeof header, "P3\n%zu %zu\n255\n", num_cols, num_rows);
+    const size_t file_size = num_cols * num_rows * kPixelNumBytes + static_cast<size_t>(header_len);  // writer.zig:20
+    MmapHandlePosix handle(out_path, file_size);
+    uint64_t content = 0;
+    if (wrt_format_ppm(ctx, rgb, static_cast<uint32_t>(num_cols), static_cast<uint32_t>(num_rows), handle.ptr, file_size, &content) != WRT_OK)
+        throw std::runtime_error(std::string("wrt_format_ppm: ") + wrt_last_error(ctx));
+    if (truncate_to_content) handle.shrink(static_cast<size_t>(content));
+    return static_cast<size_t>(content);
+}
+
 }  // namespace wrh

@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../include/wrt.h"
 #include "wrh_math.hpp"
 
 namespace wrh {
@@ -51,6 +52,9 @@ struct WriterPPM {  // writer.zig:6-52
     size_t write(const std::string& out_path, const Real* data, size_t lanes, size_t num_cols, size_t num_rows) const;
     // Same file from an already quantised frame (3 bytes per pixel, e.g. the device's fused final pass).
     size_t writeQuantised(const std::string& out_path, const uint8_t* rgb, size_t num_cols, size_t num_rows) const;
+    // Same file, formatted by the back end (wrt_format_ppm) straight into the mapping: the frame of the last render
+    // (rgb == nullptr) or the given quantised frame.  No host threads, no serial size pre-pass.
+    size_t writeOnDevice(wrt_ctx* ctx, const std::string& out_path, const uint8_t* rgb, size_t num_cols, size_t num_rows) const;
 };
 
 }  // namespace wrh
