@@ -767,8 +767,10 @@ __device__ __forceinline__ void sphere_uv(d3 v, double& u_out, double& v_out) {
 
 // Rebuild the HitRecord of the winning primitive with the reference's arithmetic (entity.zig:613-620, 490-498,
 // hitrecord.zig:16-21), then carry point and normal back out through the transform chain (entity.zig:105-107,
-// 184-186).  `want_uv` = the sphere UV (acos + atan2) is only evaluated when a texture will read it.
-__device__ inline void resolve_hit(const DeviceScene& S, const ClosestHit& ch, d3 wo, d3 wd, double time, bool want_uv, HitRecord& rec) {
+// 184-186).  `want_uv` = the sphere UV (acos + atan2) is only evaluated when a texture will read it; `want_quad_uv` likewise
+// for the quad's (alpha, beta).
+__device__ inline void resolve_hit(const DeviceScene& S, const ClosestHit& ch, d3 wo, d3 wd, double time, bool want_uv, HitRecord& rec,
+                                   bool want_quad_uv = true) {
     const uint4 op = __ldg(S.ops + ch.pc);
     d3 o, d;
     ray_in_xform(S, ch.xform, wo, wd, o, d);
@@ -792,8 +794,11 @@ __device__ inline void resolve_hit(const DeviceScene& S, const ClosestHit& ch, d
     } else {
         const QuadGeom q = S.quads[op.y];
         d3 planar = rec.point - mk(q.sx, q.sy, q.sz);
-        rec.u = dot(mk(q.wx, q.wy, q.wz), cross(planar, mk(q.vx, q.vy, q.vz)));
-        rec.v = dot(mk(q.wx, q.wy, q.wz), cross(mk(q.ux, q.uy, q.uz), planar));
+        rec.u = 0; rec.v = 0;
+        if (want_quad_uv) {  // alpha / beta again, as the texture coordinates (entity.zig:490-498); skipped for solid colours
+            rec.u = dot(mk(q.wx, q.wy, q.wz), cross(planar, mk(q.vx, q.vy, q.vz)));
+            rec.v = dot(mk(q.wx, q.wy, q.wz), cross(mk(q.ux, q.uy, q.uz), planar));
+        }
         outward = mk(q.nx, q.ny, q.nz);
         rec.is_sphere = 0;
         rec.sphere_outward = outward;

@@ -246,9 +246,12 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
         L = L + beta * ld3(rc.background);
         return false;
     }
+    const Material M = S.materials[__ldg(&S.ops[ch.pc].z)];
+    // texture coordinates are only formed when a non-solid texture will read them
+    const bool reads_texture = M.kind == WRT_MAT_LAMBERTIAN || M.kind == WRT_MAT_ISOTROPIC || M.kind == WRT_MAT_DIFFUSE_EMISSIVE;
+    const bool textured = reads_texture && (S.textures[M.texture].kind != WRT_TEX_SOLID);
     HitRecord rec;
-    resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec);
-    const Material M = S.materials[rec.material];
+    resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec, textured);
     if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) return shade_emissive(S, rec, M, beta, L);
     if (M.kind == WRT_MAT_DIELECTRIC) return shade_dielectric(rec, M, ray, rng, bounce);
     return shade_surface(S, rec, M, ray, beta, L, rng, bounce);
