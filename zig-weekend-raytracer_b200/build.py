@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",          # binary64 ops stay unfused in source order; culling uses explicit fma()
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread",
     "--expt-relaxed-constexpr",
 ]
 

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <limits>
 
 #include "wrt_program.h"
@@ -421,8 +422,10 @@ struct Compiler {
             n.rmax[0] = p.max_x; n.rmax[1] = p.max_y; n.rmax[2] = p.max_z; n.r_end = end;
         }
     }
-    // builds the subtree over items[lo, hi) (hi - lo >= 2) into record `rec`; returns its depth in records
-    uint32_t build_sah(std::vector<BvhItem>& items, size_t lo, size_t hi, uint32_t rec, uint32_t level) {
+    // builds the subtree over items[lo, hi) (hi - lo >= 2) into record `rec`; its other hi - lo - 2 records are
+    // nodes2[free, free + hi - lo - 2) (left subtree first), so the layout does not depend on which thread builds what and
+    // large subtrees of the first levels are built concurrently.  Returns the subtree's depth in records.
+    uint32_t build_sah(std::vector<BvhItem>& items, size_t lo, size_t hi, uint32_t rec, uint32_t level, uint32_t free) {
         constexpr int kBins = 16;
         auto centroid = [](const BvhItem& it, int k) { return it.box.valid() ? 0.5 * (it.box.mn[k] + it.box.mx[k]) : 0.0; };
         Box3 cb;
@@ -479,9 +482,10 @@ struct Compiler {
             std::nth_element(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)mid, items.begin() + (ptrdiff_t)hi,
                              [&](const BvhItem& a, const BvhItem& b) { return centroid(a, axis) < centroid(b, axis); });
         }
-        uint32_t depth = 1;
         Node2 n;
         std::memset(&n, 0, sizeof n);
+        uint32_t child_rec[2] = {WRT_NONE, WRT_NONE}, child_free[2] = {free, free};
+        uint32_t next = free;
         for (int side = 0; side < 2; ++side) {
             const size_t a = side == 0 ? lo : mid, b = side == 0 ? mid : hi;
             Box3 bb;
@@ -490,24 +494,36 @@ struct Compiler {
             if (b - a == 1) {
                 set_child(n, side == 0, bb, items[a].start, items[a].end);
             } else {
-                Node2 none;
-                std::memset(&none, 0, sizeof none);
-                none.l_desc = none.r_desc = WRT_NONE;
-                out.nodes2.push_back(none);
-                const uint32_t child = (uint32_t)(out.nodes2.size() - 1);
-                depth = std::max(depth, 1 + build_sah(items, a, b, child, level + 1));
-                set_child(n, side == 0, bb, 0x80000000u | child, 0);
+                child_rec[side] = next;
+                child_free[side] = next + 1;
+                next += (uint32_t)(b - a - 1);
+                set_child(n, side == 0, bb, 0x80000000u | child_rec[side], 0);
             }
         }
         out.nodes2[rec] = n;
-        return depth;
+        uint32_t depth_l = 0, depth_r = 0;
+        const bool fork = level <= 4 && child_rec[0] != WRT_NONE && child_rec[1] != WRT_NONE && (mid - lo) >= 8192 && (hi - mid) >= 8192;
+        if (fork) {
+            auto left = std::async(std::launch::async, [&] { return build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]); });
+            depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
+            depth_l = left.get();
+        } else {
+            if (child_rec[0] != WRT_NONE) depth_l = build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]);
+            if (child_rec[1] != WRT_NONE) depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
+        }
+        return 1 + std::max(depth_l, depth_r);
     }
     void rebuild_trees() {
         const char* keep = std::getenv("WRT_REFERENCE_TREE");
         if (keep && keep[0] == '1') return;
         for (BvhRoot& r : bvh_roots) {
             if (r.items.size() < 2) continue;  // a single leaf: the reference's record is already minimal
-            const uint32_t depth = build_sah(r.items, 0, r.items.size(), r.record, 1);
+            const uint32_t free = (uint32_t)out.nodes2.size();
+            Node2 none;
+            std::memset(&none, 0, sizeof none);
+            none.l_desc = none.r_desc = WRT_NONE;
+            out.nodes2.resize(out.nodes2.size() + r.items.size() - 2, none);  // a tree over n leaves has n - 1 records, one is r.record
+            const uint32_t depth = build_sah(r.items, 0, r.items.size(), r.record, 1, free);
             out.max_nesting = std::max(out.max_nesting, r.nest + depth);
         }
     }
