@@ -103,6 +103,7 @@ struct wrt_ctx {
     DevBuf<wrt::Texture> d_textures;
     DevBuf<wrt::ImageDesc> d_images;
     DevBuf<wrt::Light> d_lights;
+    DevBuf<wrt::BoxTight> d_light_boxes;
     DevBuf<uint32_t> d_sobol_matrices;
     DevBuf<wrt::SobolLut> d_sobol_lut;
     std::vector<cudaArray_t> arrays;
@@ -202,7 +203,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->free_images();
     ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
-    ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
+    ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
     ctx->d_ppm_in.release(); ctx->d_ppm_body.release(); ctx->d_ppm_blocks.release(); ctx->d_ppm_offsets.release();
     ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_counters.release();
@@ -294,12 +295,13 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     CU(ctx->d_materials.upload(cs.materials, ctx->stream));
     CU(ctx->d_textures.upload(cs.textures, ctx->stream));
     CU(ctx->d_lights.upload(cs.lights, ctx->stream));
+    CU(ctx->d_light_boxes.upload(cs.light_boxes, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     wrt::DeviceScene& ds = ctx->ds;
     ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p; ds.nodes2 = ctx->d_nodes2.p;
     ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
     ds.xforms = ctx->d_xforms.p; ds.xform_chains = ctx->d_xform_chains.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
-    ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p;
+    ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p; ds.light_boxes = ctx->d_light_boxes.p;
     ds.n_ops = (uint32_t)cs.ops.size();
     ds.n_lights = (uint32_t)cs.lights.size();
     ds.has_lights = cs.has_lights ? 1u : 0u;

@@ -98,6 +98,7 @@ struct DeviceScene {
     const Texture* textures;
     const ImageDesc* images;
     const Light* lights;
+    const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
     uint32_t use_ordered, _pad0, _pad1, _pad2;  // ordered traversal allowed (tree depth fits WRT_STACK_DEPTH)
 };
@@ -363,7 +364,10 @@ struct Culler<WRT_CULL_TIGHT> {
         err = fmaxf(fmaxf(fabsf(oi_x), fabsf(oi_y)), fabsf(oi_z)) * 4.8e-7f;
     }
     __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
-        const float4* p = reinterpret_cast<const float4*>(S.boxes_tight + box);
+        return pass_box(S.boxes_tight + box, tmin, tmax);
+    }
+    __device__ __forceinline__ bool pass_box(const BoxTight* __restrict__ b, double tmin, double tmax) const {
+        const float4* p = reinterpret_cast<const float4*>(b);
         const float4 lo4 = __ldg(p), hi4 = __ldg(p + 1);  // (min.x, min.y, min.z, -), (max.x, max.y, max.z, -)
         const float ax = fmaf(lo4.x, inv_x, -oi_x), bx = fmaf(hi4.x, inv_x, -oi_x);
         const float ay = fmaf(lo4.y, inv_y, -oi_y), by = fmaf(hi4.y, inv_y, -oi_y);
@@ -867,9 +871,10 @@ __device__ inline d3 texture_value(const DeviceScene& S, uint32_t tex, double u,
 // ---------------------------------------------------------------------------------------------------------
 // Light sampling hooks (entity.zig:371-386, 503-525, 626-651, 668-679) and PDFs (pdf.zig)
 // ---------------------------------------------------------------------------------------------------------
-__device__ inline double light_pdf_value_one(const DeviceScene& S, const Light L, d3 origin, d3 direction) {
+__device__ inline double light_pdf_value_one(const SphereGeom* __restrict__ spheres, const QuadGeom* __restrict__ quads, const Light L,
+                                             d3 origin, d3 direction) {
     if (L.kind == WRT_ENT_QUAD) {
-        const QuadGeom q = S.quads[L.index];
+        const QuadGeom q = quads[L.index];
         d3 n = mk(q.nx, q.ny, q.nz);
         double denom = dot(n, direction);
         if (fabs(denom) < 1e-8) return 0.0;
@@ -889,7 +894,7 @@ __device__ inline double light_pdf_value_one(const DeviceScene& S, const Light L
         return dist_sq / (cosine * q.area);
     }
     if (L.kind == WRT_ENT_SPHERE) {
-        const SphereGeom g = S.spheres[L.index];
+        const SphereGeom g = spheres[L.index];
         d3 center = mk(g.cx, g.cy, g.cz);
         d3 oc = center - origin;
         double a = dot(direction, direction);
@@ -912,10 +917,24 @@ __device__ inline double light_pdf_value_one(const DeviceScene& S, const Light L
     return 0.0;  // entity.zig:47-55
 }
 
-__device__ inline double lights_pdf_value(const DeviceScene& S, d3 origin, d3 direction) {  // entity.zig:371-378
+// entity.zig:371-378.  MANY = the kernel may meet long light lists (the per-lane kernels of large scenes): a light the ray
+// certainly misses contributes weight * 0.0 = +0, which leaves the sum's bits alone, so it is skipped on the strength of
+// the conservative binary32 box test (both hit tests start at tmin = 1e-3).  The packet kernels (small programs, a
+// handful of lights, 80-register budget) are compiled without that path.
+template <bool MANY>
+__device__ __forceinline__ double lights_pdf_value(const DeviceScene& S, d3 origin, d3 direction) {
     const double weight = 1.0 / (double)S.n_lights;
     double sum = 0.0;
-    for (uint32_t i = 0; i < S.n_lights; ++i) sum += weight * light_pdf_value_one(S, S.lights[i], origin, direction);
+    if (MANY && S.n_lights > 4) {
+        Culler<WRT_CULL_TIGHT> cull;
+        cull.set_ray(origin, direction);
+        for (uint32_t i = 0; i < S.n_lights; ++i) {
+            if (!cull.pass_box(S.light_boxes + i, 1e-3, CUDART_INF)) continue;
+            sum += weight * light_pdf_value_one(S.spheres, S.quads, S.lights[i], origin, direction);
+        }
+        return sum;
+    }
+    for (uint32_t i = 0; i < S.n_lights; ++i) sum += weight * light_pdf_value_one(S.spheres, S.quads, S.lights[i], origin, direction);
     return sum;
 }
 

@@ -141,6 +141,7 @@ __device__ __forceinline__ bool shade_dielectric(const HitRecord& rec, const Mat
 // Metal, lambertian and isotropic surfaces.  All direction sampling (cosine lobe, uniform sphere, cone towards a sphere
 // light) funnels through ONE sincos + ONE orthonormal-basis site, selected per lane, so the lanes of a warp stay together
 // whatever they sample.
+template <bool MANY_LIGHTS = false>
 __device__ __forceinline__ bool shade_surface(const DeviceScene& S, const HitRecord& rec, const Material& M, Ray& ray, d3& beta, d3& L,
                                               const Rng& rng, uint32_t bounce) {
     const uint32_t block_a = 2u + 2u * bounce, block_b = block_a + 1u;
@@ -228,7 +229,7 @@ __device__ __forceinline__ bool shade_surface(const DeviceScene& S, const HitRec
     const d3 dir_unit = normalize(dir);
     const double surface_pdf = cosine_pdf ? fmax(0.0, dot(dir_unit, w_n) / WRT_PI) : 1.0 / (4.0 * WRT_PI);  // pdf.zig:58-61, 36-38
     double pdf_value = surface_pdf;
-    if (S.has_lights) pdf_value = 0.5 * lights_pdf_value(S, rec.point, dir) + 0.5 * surface_pdf;  // MixturePdf.value, pdf.zig:106-111
+    if (S.has_lights) pdf_value = 0.5 * lights_pdf_value<MANY_LIGHTS>(S, rec.point, dir) + 0.5 * surface_pdf;  // MixturePdf.value, pdf.zig:106-111
     double sp;  // material.scatteringPdf, material.zig:118-125 / 145-150
     if (M.kind == WRT_MAT_LAMBERTIAN) sp = fmax(0.0, dot(rec.normal, dir_unit) / WRT_PI);
     else sp = 1.0 / (4.0 * WRT_PI);
@@ -240,6 +241,7 @@ __device__ __forceinline__ bool shade_surface(const DeviceScene& S, const HitRec
 }
 
 // All classes in one call (megakernel).
+template <bool MANY_LIGHTS = false>
 __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstants& rc, const ClosestHit& ch, Ray& ray, d3& beta, d3& L,
                                       const Rng& rng, uint32_t bounce) {
     if (ch.pc == WRT_NONE) {  // render.zig:215-217
@@ -254,7 +256,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
     resolve_hit(S, ch, ray.o, ray.d, ray.time, false, rec, textured);
     if (M.kind == WRT_MAT_DIFFUSE_EMISSIVE) return shade_emissive(S, rec, M, beta, L);
     if (M.kind == WRT_MAT_DIELECTRIC) return shade_dielectric(rec, M, ray, rng, bounce);
-    return shade_surface(S, rec, M, ray, beta, L, rng, bounce);
+    return shade_surface<MANY_LIGHTS>(S, rec, M, ray, beta, L, rng, bounce);
 }
 
 enum { TRAV_LANE = 0, TRAV_PACKET = 1 };
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 if (alive) ch = closest_hit_lane<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
                 if (alive) {
                     ++n_rays;
-                    const bool cont = shade(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
+                    const bool cont = shade<true>(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
                     --depth_left;
                     if (!cont || depth_left == 0) {
                         if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight

@@ -386,6 +386,10 @@ struct Compiler {
                 l.kind = e.kind;  // pdfValue 0, direction (1,0,0): entity.zig:47-65
             }
             out.lights.push_back(l);
+            Box3 lb;
+            lb.reset();  // stays empty (nothing passes) for the kinds whose pdfValue is 0
+            if ((e.kind == WRT_ENT_SPHERE || e.kind == WRT_ENT_QUAD) && !tight_box(id, lb)) return false;
+            out.light_boxes.push_back(padded(lb));
             return true;
         };
         if (L.kind == WRT_ENT_COLLECTION) {

@@ -23,6 +23,7 @@ struct CompiledScene {
     std::vector<Material> materials;
     std::vector<Texture> textures;
     std::vector<Light> lights;
+    std::vector<BoxTight> light_boxes;  // conservative binary32 box of every light (an empty box for kinds whose pdf is 0)
     uint32_t n_prims = 0;
     uint32_t max_xform_depth = 0;
     uint32_t max_nesting = 0;  // deepest chain of bvh_node / instance ops
