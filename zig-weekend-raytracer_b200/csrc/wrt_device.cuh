@@ -61,6 +61,9 @@ struct __align__(16) QuadGeom {   // entity.zig:431-441
     double ux, uy, uz, _p0;       // basis.u
     double vx, vy, vz, _p1;       // basis.v
     double wx, wy, wz, _p2;       // basis.w
+    // alpha = w . (planar x v) = planar . (v x w) and beta = w . (u x planar) = planar . (w x u) as plain functionals, for
+    // the interior PRE-test of the traversals (wrt_program.cu forms them in binary64)
+    double ax, ay, az, bx, by, bz;
 };
 struct __align__(16) Xform {      // Translate / RotateY chain (entity.zig:68-205)
     double a, b, c;               // translate: offset xyz; rotate_y: sin, cos, 0
@@ -399,6 +402,27 @@ __device__ __forceinline__ double div_zero_aware(double x, double y) {
     return x / y;
 }
 
+// isInteriorPoint (entity.zig:527-541) decides on alpha = w . (planar x v) and beta = w . (u x planar), 28 binary64
+// operations after 6 loads.  Both are linear in `planar`, so alpha' = planar . (v x w) and beta' = planar . (w x u) — 10
+// operations, 3 loads — equal them up to rounding (a few 1e-16 times the size of the terms).  The traversals decide on
+// (alpha', beta') whenever they are at least 1e-6 (1 + |.|) away from 0 and 1 — nine orders of magnitude above that
+// rounding — and evaluate the reference's expressions only inside that band, so every decision is the reference's.
+// `g` = the quad's record, `planar` = hit point - start.
+__device__ __forceinline__ bool quad_interior(const double2* __restrict__ g, d3 planar) {
+    const double2 c0 = __ldg(g + 10), c1 = __ldg(g + 11), c2 = __ldg(g + 12);
+    const double a1 = dot(planar, mk(c0.x, c0.y, c1.x));
+    const double b1 = dot(planar, mk(c1.y, c2.x, c2.y));
+    const double ma = 1e-6 * (1.0 + fabs(a1)), mb = 1e-6 * (1.0 + fabs(b1));
+    const bool inside = (a1 >= ma) && (a1 <= 1.0 - ma) && (b1 >= mb) && (b1 <= 1.0 - mb);
+    const bool outside = (a1 < -ma) || (a1 > 1.0 + ma) || (b1 < -mb) || (b1 > 1.0 + mb);
+    if (inside || outside) return inside;
+    const double2 u0 = __ldg(g + 4), u1 = __ldg(g + 5), v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+    const d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
+    const double alpha = dot(bw, cross(planar, bv));
+    const double beta = dot(bw, cross(bu, planar));
+    return (0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0);
+}
+
 struct ClosestHit {
     double t;
     uint32_t pc;     // op index of the winning primitive, WRT_NONE = miss
@@ -606,14 +630,10 @@ __device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, ui
         if (!(fabs(denom) < 1e-8)) {
             double t = div_zero_aware(n1.y - dot(n, o), denom);
             if ((tmin <= t) && (t <= T.best_t)) {
-                double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
-                double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);
                 d3 p = o + d * t;
                 d3 planar = p - mk(s0.x, s0.y, s1.x);
-                d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
-                double alpha = dot(bw, cross(planar, bv));
-                double beta = dot(bw, cross(bu, planar));
-                if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
+                if (quad_interior(g, planar)) {
                     if (t < T.best_t) { T.best_t = t; T.first_pc = pc; T.first_xf = T.xf; T.lastq_pc = pc; T.lastq_xf = T.xf; }
                     else {
                         if (pc < T.first_pc) { T.first_pc = pc; T.first_xf = T.xf; }
@@ -730,16 +750,10 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
                 if (!(fabs(denom) < 1e-8)) {
                     double t = div_zero_aware(n1.y - dot(n, o), denom);
                     if ((tmin <= t) && (t <= best.t)) {
-                        double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
-                        double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                        double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);
                         d3 p = o + d * t;
                         d3 planar = p - mk(s0.x, s0.y, s1.x);
-                        d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
-                        double alpha = dot(bw, cross(planar, bv));
-                        double beta = dot(bw, cross(bu, planar));
-                        if ((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0)) {
-                            best.t = t; best.pc = pc; best.xform = xf;
-                        }
+                        if (quad_interior(g, planar)) { best.t = t; best.pc = pc; best.xform = xf; }
                     }
                 }
             }

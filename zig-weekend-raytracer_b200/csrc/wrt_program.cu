@@ -358,6 +358,8 @@ struct Compiler {
             g.ux = q.u[0]; g.uy = q.u[1]; g.uz = q.u[2]; g._p0 = 0;
             g.vx = q.v[0]; g.vy = q.v[1]; g.vz = q.v[2]; g._p1 = 0;
             g.wx = q.w[0]; g.wy = q.w[1]; g.wz = q.w[2]; g._p2 = 0;
+            g.ax = g.vy * g.wz - g.vz * g.wy; g.ay = g.vz * g.wx - g.vx * g.wz; g.az = g.vx * g.wy - g.vy * g.wx;  // v x w
+            g.bx = g.wy * g.uz - g.wz * g.uy; g.by = g.wz * g.ux - g.wx * g.uz; g.bz = g.wx * g.uy - g.wy * g.ux;  // w x u
             out.quads[i] = g;
         }
         return true;
