@@ -1,14 +1,15 @@
 // wrt_kernels.cu — sm_100a kernels of the render back end.
 //
-//   render_kernel<CULL,TRAV> persistent warps pull (row, 32-column block, sample chunk) jobs — the reference's job
-//                            shape (render.zig:55-73) times a sample split — and run the iterative form of rayColor
-//                            (render.zig:188-289).  Each lane owns one pixel of the block and
-//                            regenerates a new camera sample as soon as its path ends, so lanes never idle while
-//                            the pixel still has samples; per-(pixel, chunk) sums go to a private slot.
-//                            TRAV selects the closest-hit scan: warp-uniform packet (small programs) or per-lane.
+//   render_kernel<CULL,TRAV> persistent warps run the iterative form of rayColor (render.zig:188-289).
+//                            TRAV = packet: small programs, warp-uniform scan, work drawn per LANE as (pixel, sample chunk);
+//                            TRAV = lane: large programs, ordered per-lane traversal, work drawn per warp as the reference's
+//                            (row, 32-column block) jobs (render.zig:55-73) times a sample chunk.  A lane regenerates a
+//                            camera sample as soon as its path ends; per-(pixel, chunk) sums go to a private slot.
+//   render_kernel_sync / _regroup, wf_* kernels   alternative schedules of the same functions.
 //   resolve_kernel           fused final pass: clear colour + ordered sum of the chunk slots -> caller's f64
 //                            framebuffer layout, and encodeColor (writer.zig:68-94) into RGB8.
-//   primary_hits_kernel / trace_rays_kernel / sobol_*_kernel   gates and diagnostics (include/wrt.h).
+//   ppm_*_kernel             the PPM writer's body: block sizes, scan, formatting (writer.zig:16-123).
+//   primary_hits_kernel / trace_rays_kernel / sobol_*_kernel / fp*_peak_kernel   gates and diagnostics (include/wrt.h).
 #include <math_constants.h>
 
 #include <type_traits>
