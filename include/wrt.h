@@ -241,6 +241,21 @@ WRT_API uint32_t wrt_abi_version(void);
  * traversal program and copies everything to the device. */
 WRT_API int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene);
 
+/* Host-only: compiles `scene` exactly as wrt_upload_scene does (no device, no context) and checks the result's structure —
+ * skip links, transform nesting, the packet program against the full one, every ordered-traversal tree reaching each
+ * primitive of its BVH exactly once.  Returns WRT_OK, or an error code with the reason in err[0..err_cap). */
+typedef struct wrt_scene_info {
+    uint32_t n_ops;          /* ops of the traversal program (OP_END included) */
+    uint32_t n_ops_packet;   /* ops of the pruned program the packet scan reads */
+    uint32_t n_prims;
+    uint32_t n_boxes;        /* bvh_node + instance bounds */
+    uint32_t n_tree_records; /* child-pair records of the ordered-traversal trees */
+    uint32_t tree_depth;     /* deepest tree, in records */
+    uint32_t max_nesting;    /* stack bound of the ordered traversal */
+    uint32_t n_lights;
+} wrt_scene_info;
+WRT_API int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, char* err, size_t err_cap);
+
 /* Render (replaces Renderer.render, src/render.zig:29-74) ------------------------------------- */
 /* Host framebuffer: `framebuffer` points at Framebuffer.buffer ([]Color, camera.zig:14); one pixel every
  * `pixel_stride_bytes` bytes (= @sizeOf(Vec3): 32 with 4 lanes, 64 with 8; >= 24), lanes 0..2 = R,G,B

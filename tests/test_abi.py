@@ -55,6 +55,8 @@ def test_ctypes_mirror_matches_c_layout(wrt, tmp_path):
         "wrt_params": (wrt.Params, ["width", "height", "samples_per_pixel", "max_ray_bounce_depth", "background_color",
                                     "clear_color", "seed", "row_shard_index", "row_shard_count", "sample_begin", "sample_end",
                                     "cull_mode", "flags"]),
+        "wrt_scene_info": (wrt.SceneInfo, ["n_ops", "n_ops_packet", "n_prims", "n_boxes", "n_tree_records", "tree_depth", "max_nesting",
+                                           "n_lights"]),
         "wrt_stats": (wrt.Stats, ["paths", "rays", "render_ms", "kernel_ms", "upload_ms", "kernel_launches", "program_ops",
                                   "n_prims", "traversal_steps"]),
     }

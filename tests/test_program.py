@@ -1,0 +1,62 @@
+"""Host-side compilation of the entity tree (csrc/wrt_program.cu) without a GPU: wrt_check_scene compiles a scene exactly
+as wrt_upload_scene does and checks the structure of what the kernels will read — the DFS program and its skip links,
+the pruned packet program, and the SAH trees of the ordered traversal (every primitive of a BVH reachable exactly once)."""
+from __future__ import annotations
+
+import os
+
+import pytest
+
+
+SCENES = [("cornell_box", 0), ("emissive", 0), ("shrek_quads", 0), ("earth", 0), ("balls", 0), ("rtw_final", 0),
+          ("synthetic", 4096), ("synthetic", 50000)]
+
+
+@pytest.mark.parametrize("name,n_prims", SCENES)
+def test_compiled_scene_is_structurally_sound(wrt, wro, images, name, n_prims):
+    sc = wro.OracleScene(name, seed=1, n_prims=n_prims, images=images)
+    info = wrt.check_scene(sc.flatten())
+    assert info.n_prims == sc.n_prims
+    assert info.n_ops >= info.n_prims + 1                      # every primitive has an op, plus OP_END
+    assert info.n_ops_packet <= info.n_ops
+    assert info.tree_depth <= info.max_nesting or info.tree_depth <= 2
+    if info.n_prims >= 64:                                     # a SAH tree over n leaves stays shallow
+        assert info.tree_depth <= 4 * max(1, info.n_prims).bit_length()
+    sc.close()
+
+
+def test_cornell_box_programs(wrt, wro):
+    """The Cornell box is the headline workload: 13 primitives, a 27-op reference program (SURVEY.md A.10 topology), and the
+    19-op packet program after pruning (7 of its 8 bvh_node boxes are the whole room; POP,POP fused)."""
+    sc = wro.OracleScene("cornell_box")
+    info = wrt.check_scene(sc.flatten())
+    assert (info.n_prims, info.n_ops, info.n_ops_packet, info.n_lights) == (13, 27, 19, 2)
+    sc.close()
+
+
+def test_reference_tree_switch_keeps_the_reference_topology(wrt, wro):
+    sc = wro.OracleScene("balls", seed=1)
+    flat = sc.flatten()
+    sah = wrt.check_scene(flat)
+    os.environ["WRT_REFERENCE_TREE"] = "1"
+    try:
+        ref = wrt.check_scene(flat)
+    finally:
+        del os.environ["WRT_REFERENCE_TREE"]
+    assert (ref.n_ops, ref.n_prims) == (sah.n_ops, sah.n_prims)
+    assert ref.n_tree_records <= sah.n_tree_records           # the rebuilt trees append their records
+    assert ref.tree_depth == 9                                 # balanced median split over 484 + 4 leaves (entity.zig:226-259)
+    sc.close()
+
+
+def test_invalid_scenes_are_rejected_with_a_reason(wrt, wro):
+    sc = wro.OracleScene("emissive")
+    flat = sc.flatten()
+    good_root = flat.root
+    flat.root = flat.n_entities + 5
+    with pytest.raises(wrt.WrtError) as ei:
+        wrt.check_scene(flat)
+    assert "root" in ei.value.message
+    flat.root = good_root
+    wrt.check_scene(flat)
+    sc.close()

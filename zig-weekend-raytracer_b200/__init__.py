@@ -25,7 +25,7 @@ from .abi import Camera, Params, Scene, Stats
 ABI_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_upload_scene", "wrt_render",
     "wrt_render_device", "wrt_encode_rgb8", "wrt_primary_hits", "wrt_trace_rays", "wrt_sobol_pixel_samples",
-    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm",
+    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm", "wrt_check_scene",
 ]
 
 
@@ -61,6 +61,7 @@ def _load() -> C.CDLL:
     lib.wrt_fp64_issue_peak.argtypes = [vp, vp]
     lib.wrt_fp32_issue_peak.argtypes = [vp, vp]
     lib.wrt_format_ppm.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
+    lib.wrt_check_scene.argtypes = [vp, vp, C.c_char_p, C.c_size_t]
     for name in ABI_SYMBOLS:
         if name not in ("wrt_destroy", "wrt_last_error", "wrt_abi_version"):
             getattr(lib, name).restype = C.c_int
@@ -68,6 +69,16 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+
+def check_scene(scene) -> "SceneInfo":
+    """Compile `scene` on the host (no device needed) and check the structure of the result; raises WrtError."""
+    info = SceneInfo()
+    err = C.create_string_buffer(512)
+    rc = lib.wrt_check_scene(C.addressof(scene), C.addressof(info), err, len(err))
+    if rc != 0:
+        raise WrtError(rc, err.value.decode(errors="replace"))
+    return info
 
 
 def _ptr(a):

@@ -90,6 +90,11 @@ class Params(C.Structure):
                 ("flags", C.c_uint32)]
 
 
+class SceneInfo(C.Structure):
+    _fields_ = [("n_ops", C.c_uint32), ("n_ops_packet", C.c_uint32), ("n_prims", C.c_uint32), ("n_boxes", C.c_uint32),
+                ("n_tree_records", C.c_uint32), ("tree_depth", C.c_uint32), ("max_nesting", C.c_uint32), ("n_lights", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("render_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("kernel_launches", C.c_uint32), ("program_ops", C.c_uint32),

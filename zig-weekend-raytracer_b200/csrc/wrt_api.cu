@@ -154,6 +154,28 @@ static int bind_device(wrt_ctx* ctx) {
 
 extern "C" uint32_t wrt_abi_version(void) { return WRT_ABI_VERSION; }
 
+extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, char* err, size_t err_cap) {
+    auto report = [&](const std::string& msg) {
+        if (err && err_cap) { std::snprintf(err, err_cap, "%s", msg.c_str()); }
+    };
+    if (err && err_cap) err[0] = 0;
+    if (!scene || !info) { report("scene / info is NULL"); return WRT_E_INVALID; }
+    wrt::CompiledScene cs;
+    std::string msg;
+    const int rc = wrt::compile_scene(scene, cs, msg);
+    if (rc != WRT_OK) { report(msg); return rc; }
+    std::memset(info, 0, sizeof *info);
+    info->n_ops = (uint32_t)cs.ops.size();
+    info->n_ops_packet = (uint32_t)(cs.ops_pruned.empty() ? cs.ops.size() : cs.ops_pruned.size());
+    info->n_prims = cs.n_prims;
+    info->n_boxes = (uint32_t)cs.boxes_tight.size();
+    info->n_tree_records = (uint32_t)cs.nodes2.size();
+    info->max_nesting = cs.max_nesting;
+    info->n_lights = (uint32_t)cs.lights.size();
+    if (!wrt::check_compiled_scene(cs, info->tree_depth, msg)) { report(msg); return WRT_E_STATE; }
+    return WRT_OK;
+}
+
 extern "C" const char* wrt_last_error(const wrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int wrt_create(int cuda_device, wrt_ctx** out) {

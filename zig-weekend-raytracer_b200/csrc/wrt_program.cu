@@ -656,6 +656,113 @@ struct Compiler {
 
 }  // namespace
 
+namespace {
+
+bool check_program(const std::vector<uint4>& ops, const char* what, std::string& err) {
+    const size_t n = ops.size();
+    if (n == 0 || ops[n - 1].x != OP_END) { err = std::string(what) + ": program does not end in OP_END"; return false; }
+    int depth = 0;
+    for (size_t pc = 0; pc < n; ++pc) {
+        const uint4 op = ops[pc];
+        if (op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) {
+            if (!(op.z > pc && op.z <= n - 1)) { err = std::string(what) + ": skip link out of range at op " + std::to_string(pc); return false; }
+        } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
+            ++depth;
+        } else if (op.x == OP_POP) {
+            if (--depth < 0) { err = std::string(what) + ": unbalanced POP at op " + std::to_string(pc); return false; }
+        } else if (op.x == OP_END && pc != n - 1) {
+            err = std::string(what) + ": OP_END in the middle"; return false;
+        } else if (op.x > OP_NODE_TIGHT_ONLY) {
+            err = std::string(what) + ": unknown op kind"; return false;
+        }
+    }
+    // a POP may have been fused away in the packet program: the remaining ones must still close every frame they leave
+    return true;
+}
+
+}  // namespace
+
+bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::string& err) {
+    tree_depth = 0;
+    if (!check_program(cs.ops, "ops", err)) return false;
+    const size_t n = cs.ops.size();
+    if (!cs.ops_pruned.empty()) {
+        // the packet program holds the same primitive and transform-entry ops in the same order; nodes and POPs may be fewer
+        size_t j = 0;
+        for (size_t pc = 0; pc < n; ++pc) {
+            const uint4 op = cs.ops[pc];
+            if (op.x != OP_SPHERE && op.x != OP_QUAD && op.x != OP_PUSH_TRANSLATE && op.x != OP_PUSH_ROTATE_Y) continue;
+            while (j < cs.ops_pruned.size() && cs.ops_pruned[j].x != OP_SPHERE && cs.ops_pruned[j].x != OP_QUAD &&
+                   cs.ops_pruned[j].x != OP_PUSH_TRANSLATE && cs.ops_pruned[j].x != OP_PUSH_ROTATE_Y) ++j;
+            if (j == cs.ops_pruned.size() || cs.ops_pruned[j].x != op.x || cs.ops_pruned[j].y != op.y ||
+                ((op.x == OP_SPHERE || op.x == OP_QUAD) && (cs.ops_pruned[j].z != op.z || cs.ops_pruned[j].w != op.w))) {
+                err = "packet program differs from ops at op " + std::to_string(pc); return false;
+            }
+            ++j;
+        }
+        const size_t np = cs.ops_pruned.size();
+        if (np == 0 || cs.ops_pruned[np - 1].x != OP_END) { err = "packet program does not end in OP_END"; return false; }
+        for (size_t pc = 0; pc < np; ++pc) {
+            const uint4 op = cs.ops_pruned[pc];
+            if ((op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) && !(op.z > pc && op.z <= np - 1)) {
+                err = "packet program: skip link out of range at op " + std::to_string(pc); return false;
+            }
+        }
+    }
+    // ordered-traversal trees: from every bvh root (an OP_NODE not enclosed by another OP_NODE's own tree) the records must
+    // reach each primitive op of [pc + 1, skip) exactly once (nested trees are entered through their own root op)
+    std::vector<uint8_t> seen(n, 0);
+    std::vector<uint8_t> is_root(n, 0);
+    {   // a root = an OP_NODE that is not a direct descendant bvh_node of an open OP_NODE without a frame / collection boundary;
+        // the traversal itself tells: roots are the OP_NODE ops it meets INSIDE leaf ranges, plus op 0
+        std::vector<std::pair<uint32_t, uint32_t>> ranges;  // leaf op ranges still to scan for nested roots
+        ranges.push_back({0u, (uint32_t)n - 1});
+        while (!ranges.empty()) {
+            auto [lo, hi] = ranges.back();
+            ranges.pop_back();
+            for (uint32_t pc = lo; pc < hi;) {
+                const uint4 op = cs.ops[pc];
+                if (op.x != OP_NODE) {
+                    if (op.x == OP_SPHERE || op.x == OP_QUAD) {
+                        if (seen[pc]++) { err = "primitive op " + std::to_string(pc) + " reached twice"; return false; }
+                    }
+                    ++pc;
+                    continue;
+                }
+                is_root[pc] = 1;
+                // walk this tree's records
+                struct Item { uint32_t rec, depth; };
+                std::vector<Item> st;
+                st.push_back({op.y, 1u});
+                size_t visited = 0;
+                while (!st.empty()) {
+                    const Item it = st.back();
+                    st.pop_back();
+                    if (it.rec >= cs.nodes2.size()) { err = "tree record index out of range"; return false; }
+                    if (++visited > cs.nodes2.size()) { err = "tree records form a cycle"; return false; }
+                    tree_depth = std::max(tree_depth, it.depth);
+                    const Node2& r = cs.nodes2[it.rec];
+                    const uint32_t desc[2] = {r.l_desc, r.r_desc}, end[2] = {r.l_end, r.r_end};
+                    for (int k = 0; k < 2; ++k) {
+                        if (desc[k] == WRT_NONE) { if (k == 0) { err = "tree record without a left child"; return false; } continue; }
+                        if (desc[k] & 0x80000000u) st.push_back({desc[k] & 0x7FFFFFFFu, it.depth + 1});
+                        else {
+                            if (!(desc[k] > pc && end[k] > desc[k] && end[k] <= op.z)) { err = "tree leaf range outside its bvh at op " + std::to_string(pc); return false; }
+                            ranges.push_back({desc[k], end[k]});
+                        }
+                    }
+                }
+                pc = op.z;  // the tree covered [pc + 1, skip)
+            }
+        }
+    }
+    for (size_t pc = 0; pc < n; ++pc)
+        if ((cs.ops[pc].x == OP_SPHERE || cs.ops[pc].x == OP_QUAD) && seen[pc] != 1) {
+            err = "primitive op " + std::to_string(pc) + " is not reachable through the ordered-traversal trees"; return false;
+        }
+    return true;
+}
+
 int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err) {
     out = CompiledScene();
     Compiler c(scene, out, err);

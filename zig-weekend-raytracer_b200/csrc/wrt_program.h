@@ -34,4 +34,9 @@ struct CompiledScene {
 // Returns WRT_OK or a WRT_E_* code with `err` set.
 int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err);
 
+// Structural self-check of a compiled scene (host only; wrt_check_scene, tests/test_program.py): skip links, transform
+// nesting, the packet program against the full one, and that every ordered-traversal tree reaches each primitive op of
+// its BVH exactly once.  Returns true or sets `err`.  `tree_depth` = deepest tree in records.
+bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::string& err);
+
 }  // namespace wrt
