@@ -512,6 +512,8 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         if (forced_chunks) want = std::min<uint64_t>(forced_chunks, n_samples);
         n_chunks = (uint32_t)std::max<uint64_t>(want, 1);
     }
+    if (n_pixels64 > 0 && (uint64_t)n_chunks * n_pixels64 > 0xFFFFFFFFull)  // lane jobs are indexed in 32 bits
+        n_chunks = (uint32_t)std::max<uint64_t>(0xFFFFFFFFull / n_pixels64, 1);
     rc.chunk_size = n_samples ? (n_samples + n_chunks - 1) / n_chunks : 1;
     if (rc.chunk_size == 0) rc.chunk_size = 1;
     rc.n_chunks = n_samples ? (n_samples + rc.chunk_size - 1) / rc.chunk_size : 0;
@@ -586,7 +588,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     CU(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[3]));
     CU(cudaEventElapsedTime(&ms_kernel, ctx->ev[1], ctx->ev[2]));
     ctx->stats.rays = wavefront ? wf_rays : counters[1];
-    ctx->stats.paths = wavefront ? wf_paths : counters[2];
+    // the lane-job kernel does not count paths: every (pixel, chunk) job runs all its samples
+    const bool lane_job_kernel = !wavefront && packet && !sync_engine && !regroup_engine;
+    ctx->stats.paths = wavefront ? wf_paths : (lane_job_kernel ? n_pixels64 * n_samples : counters[2]);
     ctx->stats.traversal_steps = wavefront ? 0 : counters[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;

@@ -279,10 +279,11 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
         // Packet scan: work is handed out per LANE.  A lane job is (pixel of the shard, sample chunk), and a lane that finishes its job takes
         // the next one while its neighbours are still mid-chunk, so no lane waits for the longest path sum of its warp and
         // the kernel's tail is one lane job.  The warp draws its lanes' jobs with one atomic (ballot + prefix count).
-        unsigned long long job = 0;     // this lane's job
+        uint32_t job = 0;               // this lane's job (the host keeps lane_jobs below 2^32)
         bool have_job = false, drained = false;
         uint32_t col = 0, row = 0, s = 0, s_last = 0;
-        uint32_t acc_rays = 0, acc_paths = 0;  // 32-bit tallies, flushed to the 64-bit counters every ~64 K rays and at the end
+        uint32_t acc_rays = 0;  // 32-bit tally, flushed to the 64-bit counter every ~64 K rays and at the end; paths are not
+                                // counted: every job runs all its samples, the host knows the total
         // Few values live across the traversal (the kernel runs at an 80-register cap): the job's colour sum sits in its
         // accumulator slot and is updated once per path, the radiance of a path exists only in the iteration that ends it
         // (only terminal events add radiance: emission, background, the depth cut).
@@ -301,8 +302,9 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 if ((int)lane == leader) first = atomicAdd(&counters[0], (unsigned long long)__popc(wanting));
                 first = __shfl_sync(0xffffffffu, first, leader);
                 if (want) {
-                    job = first + __popc(wanting & ((1u << lane) - 1u));
-                    if (job < rc.lane_jobs) {  // job -> (chunk, pixel of the shard); chunks outermost
+                    const unsigned long long mine = first + __popc(wanting & ((1u << lane) - 1u));
+                    job = (uint32_t)mine;
+                    if (mine < rc.lane_jobs) {  // job -> (chunk, pixel of the shard); chunks outermost
                         const uint32_t chunk = (uint32_t)(job / rc.n_pixels_local);
                         const uint32_t pix = (uint32_t)(job % rc.n_pixels_local);
                         const uint32_t local_row = pix / rc.width;
@@ -312,12 +314,9 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                         s_last = min(s + rc.chunk_size, rc.sample_end);
                         rng.pixel = row * rc.width + col;
                         have_job = true;
-                        double* slot = accum + job * 3ull;
+                        double* slot = accum + (size_t)job * 3;
                         slot[0] = 0.0; slot[1] = 0.0; slot[2] = 0.0;
-                        if (rc.max_depth == 0) {  // depth 0 returns black for every sample (render.zig:199)
-                            atomicAdd(&counters[2], (unsigned long long)(s_last - s));
-                            have_job = false;
-                        }
+                        if (rc.max_depth == 0) have_job = false;  // depth 0 returns black for every sample (render.zig:199)
                     } else {
                         drained = true;
                     }
@@ -343,22 +342,20 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 --depth_left;
                 if (!cont || depth_left == 0) {
                     if (cont) L = L + beta * 0.0;  // depth exhausted: the tail returns 0 (render.zig:199), times the weight
-                    double* slot = accum + job * 3ull;  // (chunk, pixel) slot == job index
+                    double* slot = accum + (size_t)job * 3;  // (chunk, pixel) slot == job index
                     slot[0] = slot[0] + L.x * scale;    // color += L * scale, render.zig:129-135
                     slot[1] = slot[1] + L.y * scale;
                     slot[2] = slot[2] + L.z * scale;
                     alive = false;
-                    ++acc_paths;
                     if (++s == s_last) have_job = false;  // chunk complete
                     if (acc_rays >= (1u << 16)) {
                         atomicAdd(&counters[1], (unsigned long long)acc_rays);
-                        atomicAdd(&counters[2], (unsigned long long)acc_paths);
-                        acc_rays = 0; acc_paths = 0;
+                        acc_rays = 0;
                     }
                 }
             }
         }
-        n_rays = acc_rays; n_paths = acc_paths;  // the remainder joins the warp reduction below
+        n_rays = acc_rays;  // the remainder joins the warp reduction below
     } else {
         // Per-lane scan: warp jobs (row, 32-column block, sample chunk) keep the lanes of a warp on neighbouring pixels, whose
         // traversals are of similar length; lanes still regenerate their own samples inside the job.
