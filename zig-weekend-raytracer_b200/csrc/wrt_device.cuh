@@ -405,16 +405,18 @@ __device__ __forceinline__ double div_zero_aware(double x, double y) {
 // isInteriorPoint (entity.zig:527-541) decides on alpha = w . (planar x v) and beta = w . (u x planar), 28 binary64
 // operations after 6 loads.  Both are linear in `planar`, so alpha' = planar . (v x w) and beta' = planar . (w x u) — 10
 // operations, 3 loads — equal them up to rounding (a few 1e-16 times the size of the terms).  The traversals decide on
-// (alpha', beta') whenever they are at least 1e-6 (1 + |.|) away from 0 and 1 — nine orders of magnitude above that
-// rounding — and evaluate the reference's expressions only inside that band, so every decision is the reference's.
+// (alpha', beta') whenever they are at least 2e-6 away from 0 and 1 — many orders of magnitude above that rounding — and
+// evaluate the reference's expressions only inside that band, so every decision is the reference's.
 // `g` = the quad's record, `planar` = hit point - start.
 __device__ __forceinline__ bool quad_interior(const double2* __restrict__ g, d3 planar) {
     const double2 c0 = __ldg(g + 10), c1 = __ldg(g + 11), c2 = __ldg(g + 12);
     const double a1 = dot(planar, mk(c0.x, c0.y, c1.x));
     const double b1 = dot(planar, mk(c1.y, c2.x, c2.y));
-    const double ma = 1e-6 * (1.0 + fabs(a1)), mb = 1e-6 * (1.0 + fabs(b1));
-    const bool inside = (a1 >= ma) && (a1 <= 1.0 - ma) && (b1 >= mb) && (b1 <= 1.0 - mb);
-    const bool outside = (a1 < -ma) || (a1 > 1.0 + ma) || (b1 < -mb) || (b1 > 1.0 + mb);
+    // constant bands: if neither coordinate is flagged outside, |planar| is bounded by the quad's size and the rounding is
+    // ~1e-13; if |planar| is so large that the rounding of one coordinate could reach 1e-6, the other coordinate is far
+    // outside [0,1] for the exact expressions too, so "outside" is the exact answer either way
+    const bool inside = (a1 >= 2e-6) && (a1 <= 1.0 - 2e-6) && (b1 >= 2e-6) && (b1 <= 1.0 - 2e-6);
+    const bool outside = (a1 < -2e-6) || (a1 > 1.0 + 2e-6) || (b1 < -2e-6) || (b1 > 1.0 + 2e-6);
     if (inside || outside) return inside;
     const double2 u0 = __ldg(g + 4), u1 = __ldg(g + 5), v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
     const d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
