@@ -890,24 +890,24 @@ __device__ inline d3 texture_value(const DeviceScene& S, uint32_t tex, double u,
 __device__ inline double light_pdf_value_one(const SphereGeom* __restrict__ spheres, const QuadGeom* __restrict__ quads, const Light L,
                                              d3 origin, d3 direction) {
     if (L.kind == WRT_ENT_QUAD) {
-        const QuadGeom q = quads[L.index];
-        d3 n = mk(q.nx, q.ny, q.nz);
+        const double2* g = reinterpret_cast<const double2*>(quads + L.index);
+        const double2 n0 = __ldg(g), n1 = __ldg(g + 1);
+        d3 n = mk(n0.x, n0.y, n1.x);
         double denom = dot(n, direction);
         if (fabs(denom) < 1e-8) return 0.0;
-        double t = div_zero_aware(q.offset - dot(n, origin), denom);
+        double t = div_zero_aware(n1.y - dot(n, origin), denom);
         if (!((1e-3 <= t) && (t <= CUDART_INF))) return 0.0;
+        const double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);  // start, area
         d3 p = origin + direction * t;
-        d3 planar = p - mk(q.sx, q.sy, q.sz);
-        double alpha = dot(mk(q.wx, q.wy, q.wz), cross(planar, mk(q.vx, q.vy, q.vz)));
-        double beta = dot(mk(q.wx, q.wy, q.wz), cross(mk(q.ux, q.uy, q.uz), planar));
-        if (!((0.0 <= alpha) && (alpha <= 1.0) && (0.0 <= beta) && (beta <= 1.0))) return 0.0;
+        d3 planar = p - mk(s0.x, s0.y, s1.x);
+        if (!quad_interior(reinterpret_cast<const double2*>(quads + L.index), planar)) return 0.0;
         // record.normal is the face-forwarded normal; only |dot| is used (entity.zig:515)
         double dir_length_sq = dot(direction, direction);
         double dist_sq = t * t * dir_length_sq;
         bool front = dot(direction, n) < 0.0;
         d3 nn = front ? n : -n;
         double cosine = fabs(dot(direction, nn)) / sqrt(dir_length_sq);
-        return dist_sq / (cosine * q.area);
+        return dist_sq / (cosine * s1.y);
     }
     if (L.kind == WRT_ENT_SPHERE) {
         const SphereGeom g = spheres[L.index];
