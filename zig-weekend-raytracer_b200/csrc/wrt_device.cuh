@@ -348,8 +348,10 @@ struct Culler<WRT_CULL_REFERENCE> {
 // Fast path: proper 3-axis slab intersection on boxes recomputed from the primitives.  Culling only has to be
 // conservative, never exact, so it runs in binary32 on the full-rate FP32 pipe (the FP64 pipe has half the lanes and no
 // single-instruction min/max): boxes are rounded outwards and padded at upload, the ray carries an absolute error bound
-// per axis, and the exit distance gets a relative slack.  Error budget: inv = fl(1/fl(d)) is off by
-// <= 3 ulp, o*inv and the FMA round once each, so a slab distance is off by <= (|o*inv| + |b*inv|) * 2^-22 + |t| * 2^-21.
+// per axis, and the exit distance gets a relative slack.  Error budget: inv = rcp.approx(fl(d))
+// is off by <= 3 * 2^-24 relative (2^-24 for the rounding of d, 2^-23 for MUFU.RCP), o*inv and the FMA round once each, so a
+// slab distance is off by <= (|o*inv| + |b*inv|) * 2^-22 + |t| * 2^-21; the margins used are 2x (origin term, `err`), 16x
+// (box term, the 4e-6 padding) and 4x (relative slack on the exit distance) of that.
 template <>
 struct Culler<WRT_CULL_TIGHT> {
     float inv_x, inv_y, inv_z;   // 1 / d
@@ -359,7 +361,11 @@ struct Culler<WRT_CULL_TIGHT> {
         float f = (float)v;
         // a zero / denormal component would make inv infinite and b*inv - o*inv an inf - inf NaN
         if (!(fabsf(f) >= 1e-20f)) f = copysignf(1e-20f, __double2hiint(v) < 0 ? -1.0f : 1.0f);
-        return __frcp_rn(f);
+        // one MUFU.RCP (relative error <= 2^-23; together with the rounding of f, 3 * 2^-24, inside the budget below) instead
+        // of the IEEE-rounded reciprocal and its denormal slow path
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+        return r;
     }
     __device__ __forceinline__ void set_ray(d3 ro, d3 rd) {
         inv_x = safe_inv(rd.x); inv_y = safe_inv(rd.y); inv_z = safe_inv(rd.z);
