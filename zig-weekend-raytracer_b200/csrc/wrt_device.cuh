@@ -333,6 +333,7 @@ struct Culler;
 template <>
 struct Culler<WRT_CULL_REFERENCE> {
     d3 o, d;
+    template <bool FAST = false>
     __device__ __forceinline__ void set_ray(d3 ro, d3 rd) { o = ro; d = rd; }
     __device__ __forceinline__ bool pass(const DeviceScene& S, uint32_t box, double tmin, double tmax) const {
         const double2* p = reinterpret_cast<const double2*>(S.boxes_ref + box);
@@ -348,8 +349,8 @@ struct Culler<WRT_CULL_REFERENCE> {
 // Fast path: proper 3-axis slab intersection on boxes recomputed from the primitives.  Culling only has to be
 // conservative, never exact, so it runs in binary32 on the full-rate FP32 pipe (the FP64 pipe has half the lanes and no
 // single-instruction min/max): boxes are rounded outwards and padded at upload, the ray carries an absolute error bound
-// per axis, and the exit distance gets a relative slack.  Error budget: inv = rcp.approx(fl(d))
-// is off by <= 3 * 2^-24 relative (2^-24 for the rounding of d, 2^-23 for MUFU.RCP), o*inv and the FMA round once each, so a
+// per axis, and the exit distance gets a relative slack.  Error budget: inv = rcp(fl(d)) is off
+// by <= 3 * 2^-24 relative (2^-24 for the rounding of d, up to 2^-23 for the approximate reciprocal of the packet scan), o*inv and the FMA round once each, so a
 // slab distance is off by <= (|o*inv| + |b*inv|) * 2^-22 + |t| * 2^-21; the margins used are 2x (origin term, `err`), 16x
 // (box term, the 4e-6 padding) and 4x (relative slack on the exit distance) of that.
 template <>
@@ -357,18 +358,25 @@ struct Culler<WRT_CULL_TIGHT> {
     float inv_x, inv_y, inv_z;   // 1 / d
     float oi_x, oi_y, oi_z;      // o / d
     float err;                   // max_k |o_k / d_k| * 2^-21: absolute slab-distance error of this ray (the largest axis' bound serves all three)
+    // FAST: one MUFU.RCP (relative error <= 2^-23; together with the rounding of f, 3 * 2^-24, inside the budget above)
+    // instead of the IEEE-rounded reciprocal and its denormal slow path.  Measured: +2.4 % in the packet kernel (which sits
+    // at its register cap and runs the set-up with all lanes), -9 % in the per-lane kernel — so only the packet scan asks
+    // for it.
+    template <bool FAST>
     static __device__ __forceinline__ float safe_inv(double v) {
         float f = (float)v;
         // a zero / denormal component would make inv infinite and b*inv - o*inv an inf - inf NaN
         if (!(fabsf(f) >= 1e-20f)) f = copysignf(1e-20f, __double2hiint(v) < 0 ? -1.0f : 1.0f);
-        // one MUFU.RCP (relative error <= 2^-23; together with the rounding of f, 3 * 2^-24, inside the budget below) instead
-        // of the IEEE-rounded reciprocal and its denormal slow path
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
-        return r;
+        if (FAST) {
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+            return r;
+        }
+        return __frcp_rn(f);
     }
+    template <bool FAST = false>
     __device__ __forceinline__ void set_ray(d3 ro, d3 rd) {
-        inv_x = safe_inv(rd.x); inv_y = safe_inv(rd.y); inv_z = safe_inv(rd.z);
+        inv_x = safe_inv<FAST>(rd.x); inv_y = safe_inv<FAST>(rd.y); inv_z = safe_inv<FAST>(rd.z);
         oi_x = (float)ro.x * inv_x; oi_y = (float)ro.y * inv_y; oi_z = (float)ro.z * inv_z;
         err = fmaxf(fmaxf(fabsf(oi_x), fabsf(oi_y)), fabsf(oi_z)) * 4.8e-7f;
     }
@@ -709,7 +717,7 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
     d3 o = wo, d = wd;
     uint32_t xf = WRT_NONE;
     Culler<CULL> cull;
-    cull.set_ray(o, d);
+    cull.template set_ray<true>(o, d);
     uint32_t pc = 0;      // uniform
     uint32_t resume = 0;  // per lane: first op this lane takes part in again
     for (;;) {
@@ -769,12 +777,12 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
         } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
             apply_xform(S.xforms[op.y], o, d);
             xf = op.y;
-            if (!op.z) cull.set_ray(o, d);  // z = 1 (pruned program): no box test before the next transform op
+            if (!op.z) cull.template set_ray<true>(o, d);  // z = 1 (pruned program): no box test before the next transform op
             ++pc;
         } else if (op.x == OP_POP) {
             xf = op.y;
             ray_in_xform(S, xf, wo, wd, o, d);
-            if (!op.z) cull.set_ray(o, d);
+            if (!op.z) cull.template set_ray<true>(o, d);
             ++pc;
         } else {  // OP_END
             break;
