@@ -88,6 +88,14 @@ def _load() -> C.CDLL:
     lib.wro_size_of_digit.restype = C.c_uint32
     lib.wro_counter_rng_bits.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.wro_counter_rng_bits.restype = C.c_uint64
+    lib.wro_kat_splitmix64.argtypes = [C.c_uint64, C.c_uint32, vp]
+    lib.wro_kat_splitmix64.restype = None
+    lib.wro_kat_xoshiro256pp.argtypes = [vp, C.c_uint32, vp]
+    lib.wro_kat_xoshiro256pp.restype = None
+    lib.wro_kat_default_prng.argtypes = [C.c_uint64, C.c_uint32, vp, vp]
+    lib.wro_kat_default_prng.restype = None
+    lib.wro_murmur2_hash_u32_with_seed.argtypes = [C.c_uint32, C.c_uint32]
+    lib.wro_murmur2_hash_u32_with_seed.restype = C.c_uint32
     lib.wro_math_cross.argtypes = [vp, vp, vp]
     lib.wro_math_cross.restype = None
     lib.wro_math_dot.argtypes = [vp, vp]

@@ -510,3 +510,26 @@ void wro_math_normalize(const double u[3], double out[3]) {
     v3 c = v3_normalize(arr3(u));
     out[0] = c.x; out[1] = c.y; out[2] = c.z;
 }
+
+/* ---- known-answer hooks for the restated Zig std pieces (tests/test_oracle_kats.py) ---------------------------------
+ * The generators below are what rng.zig:6,17 instantiate (std.Random.DefaultPrng = Xoshiro256++ seeded through SplitMix64);
+ * the tests pin them against the PUBLIC vectors of the algorithms' authors (Vigna's splitmix64.c / xoshiro256plusplus.c). */
+void wro_kat_splitmix64(uint64_t seed, uint32_t n, uint64_t* out) {
+    uint64_t s = seed;
+    for (uint32_t i = 0; i < n; ++i) out[i] = wro_splitmix64(&s);
+}
+void wro_kat_xoshiro256pp(const uint64_t state[4], uint32_t n, uint64_t* out) {
+    wro_rng r;
+    r.mode = WRO_RNG_REFERENCE;
+    for (int i = 0; i < 4; ++i) r.s[i] = state[i];
+    for (uint32_t i = 0; i < n; ++i) out[i] = wro_xoshiro_next(&r);
+}
+/* DefaultPrng.init(seed) followed by n draws of Random.float(f64) / next() */
+void wro_kat_default_prng(uint64_t seed, uint32_t n, uint64_t* out_u64, double* out_float) {
+    wro_rng r;
+    wro_rng_seed_reference(&r, seed);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (out_u64) out_u64[i] = wro_xoshiro_next(&r);
+        else out_float[i] = wro_rng_float(&r);
+    }
+}

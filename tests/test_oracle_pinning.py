@@ -1,0 +1,187 @@
+"""Pins of the oracle that do NOT come from the oracle itself (VERDICT r1 "parity unpinned", ADVICE r1 last item).
+
+ (1) the Zig standard-library pieces the reference leans on (rng.zig:6,17; sampler.zig:241) are not under /root/reference;
+     the oracle restates them.  They are pinned here against PUBLIC known-answer vectors of the algorithms themselves:
+       - SplitMix64: Vigna's splitmix64.c, seed 1234567 (the vector every port quotes);
+       - xoshiro256++: Vigna's xoshiro256plusplus.c with state {1,2,3,4} (the vector of the rand_xoshiro test-suite);
+       - Zig's own std/Random/Xoshiro256.zig `test "sequence"`: Xoshiro256.init(0) — covers the SplitMix64 seeding of
+         DefaultPrng.init exactly as rng.zig:17 calls it;
+       - MurmurHash2: smhasher's verification value 0x27864C1E (the value Zig's std/hash/murmur.zig test asserts),
+         computed with a byte-string implementation written here, against which the oracle's 4-byte specialisation
+         (hashUint32WithSeed, sampler.zig:241) is then compared;
+       - Philox4x32-10 (the device stream) is pinned in test_oracle_kats.py against the Random123 vector.
+ (2) hand-evaluated known answers of the reference's own formulas (entity.zig, pdf.zig, aabb.zig, material.zig), worked
+     out on paper from the cited lines — not produced by running the oracle.
+ (3) the reference's only published render (examples/cornell-10k-50-importance-sampling.png): region means of the cells the
+     changed tall box does not dominate (tests/golden/make_example_regions.py).
+"""
+from __future__ import annotations
+
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+# ---- (1) public vectors ---------------------------------------------------------------------------------------------
+def test_splitmix64_public_vector(wro):
+    out = np.zeros(5, np.uint64)
+    wro.lib.wro_kat_splitmix64(1234567, 5, wro._ptr(out))
+    assert out.tolist() == [6457827717110365317, 3203168211198807973, 9817491932198370423, 4593380528125082431,
+                            16408922859458223821]
+
+
+def test_xoshiro256plusplus_public_vector(wro):
+    state = np.array([1, 2, 3, 4], np.uint64)
+    out = np.zeros(10, np.uint64)
+    wro.lib.wro_kat_xoshiro256pp(wro._ptr(state), 10, wro._ptr(out))
+    assert out.tolist() == [41943041, 58720359, 3588806011781223, 3591011842654386, 9228616714210784205,
+                            9973669472204895162, 14011001112246962877, 12406186145184390807, 15849039046786891736,
+                            10450023813501588000]
+
+
+def test_zig_default_prng_init_zero_sequence(wro):  # std/Random/Xoshiro256.zig test "sequence": init(0)
+    out = np.zeros(8, np.uint64)
+    wro.lib.wro_kat_default_prng(0, 8, wro._ptr(out), None)
+    assert out.tolist() == [0x53175d61490b23df, 0x61da6f3dc380d507, 0x5c0fdf91ec9a7bfc, 0x02eebf8c3bbe5e1a,
+                            0x7eca04ebaf4a5eea, 0x0543c37757f08d9a, 0xdb7490c75ab5026e, 0xd87343e6464bc959]
+
+
+def test_zig_random_float_f64_bits(wro):
+    """Random.float(f64): 52 mantissa bits of one u64 + exponent 1022 - clz (std/Random.zig); evaluated by hand on the
+    init(0) stream above: 0x53175d61490b23df has clz 1 -> exponent 1021 -> value in [0.25, 0.5)."""
+    f = np.zeros(3, np.float64)
+    wro.lib.wro_kat_default_prng(0, 3, None, wro._ptr(f))
+    def want(u):
+        lz = 64 - u.bit_length()
+        assert lz < 12
+        return np.uint64(((1022 - lz) << 52) | (u & 0xFFFFFFFFFFFFF)).view(np.float64)
+    for got, u in zip(f, (0x53175d61490b23df, 0x61da6f3dc380d507, 0x5c0fdf91ec9a7bfc)):
+        assert got == want(u) and 0.0 <= got < 1.0
+
+
+def _murmur2(data: bytes, seed: int) -> int:  # MurmurHash2 (Appleby), byte-string form, written from the published algorithm
+    m, mask = 0x5bd1e995, 0xFFFFFFFF
+    h = (seed ^ len(data)) & mask
+    i = 0
+    while len(data) - i >= 4:
+        k = int.from_bytes(data[i:i + 4], "little")
+        k = (k * m) & mask; k ^= k >> 24; k = (k * m) & mask
+        h = (h * m) & mask; h ^= k
+        i += 4
+    rem = len(data) - i
+    if rem == 3: h ^= data[i + 2] << 16
+    if rem >= 2: h ^= data[i + 1] << 8
+    if rem >= 1:
+        h ^= data[i]
+        h = (h * m) & mask
+    h ^= h >> 13; h = (h * m) & mask; h ^= h >> 15
+    return h
+
+
+def test_murmur2_smhasher_verification_and_u32_specialisation(wro):
+    key = bytes(range(256))
+    hashes = b"".join(_murmur2(key[:i], 256 - i).to_bytes(4, "little") for i in range(256))
+    assert _murmur2(hashes, 0) == 0x27864C1E  # smhasher VerificationTest value of MurmurHash2
+    rng = np.random.default_rng(5)
+    for v, s in zip(rng.integers(0, 2**32, 200), rng.integers(0, 2**32, 200)):
+        assert wro.lib.wro_murmur2_hash_u32_with_seed(int(v), int(s)) == _murmur2(int(v).to_bytes(4, "little"), int(s))
+
+
+# ---- (2) hand-evaluated known answers of the reference's formulas -------------------------------------------------------
+def test_sphere_hit_record_by_hand(wro):
+    """SphereEntity.hit (entity.zig:585-623) on the Cornell glass sphere: centre (190, 90, 190), radius 90 (scene.zig:395-397).  Ray o = (190, 90, -800), d = (0, 0, 2):
+    oc = (0,0,990), a = 4, h = 1980, c = 990^2 - 8100 = 972000, disc = 1980^2 - 4*972000 = 32400, sqrt = 180,
+    root = (1980 - 180)/4 = 450 -> point (190, 90, 100), outward normal (0,0,-1), front face, uv = (0.75... , 0.5):
+    theta = acos(-0) = pi/2 -> v = 0.5; phi = atan2(1, 0) + pi = 3pi/2 -> u = 0.75 (entity.zig:659-666)."""
+    sc = wro.OracleScene("cornell_box")
+    o = np.array([[190.0, 90.0, -800.0]]); d = np.array([[0.0, 0.0, 2.0]])
+    r = sc.trace_rays(o, d, 1e-4)
+    ids, t, point, normal, uv, ff = (r[k] for k in ("prim_id", "t", "point", "normal", "uv", "front_face"))
+    kinds, mats, centers = sc.prim_table()
+    assert kinds[ids[0]] == 0 and mats[ids[0]] == 4  # the glass sphere (material 4, scene.zig:345)
+    assert t[0] == 450.0
+    np.testing.assert_array_equal(point[0], [190.0, 90.0, 100.0])
+    np.testing.assert_array_equal(normal[0], [0.0, 0.0, -1.0])
+    assert ff[0] == 1
+    np.testing.assert_allclose(uv[0], [0.75, 0.5], atol=1e-15)
+    sc.close()
+
+
+def test_quad_hit_record_by_hand(wro):
+    """QuadEntity.hit (entity.zig:477-501) on the Cornell back wall: start (0,0,555), u = (555,0,0), v = (0,555,0)
+    (scene.zig:388-392) -> n = u x v = (0,0,555^2), unit normal (0,0,1), D = 555, w = n/(n.n) = (0,0,1/555^2).
+    Ray o = (100, 200, -445), d = (0,0,4): denom = 4, t = (555 + 445)/4 = 250, planar = (100,200,0),
+    alpha = w.(planar x v) = 100/555, beta = w.(u x planar) = 200/555; the ray travels along +n so front_face is false and
+    the stored normal is -n (hitrecord.zig:16-21)."""
+    sc = wro.OracleScene("cornell_box")
+    o = np.array([[100.0, 200.0, -445.0]]); d = np.array([[0.0, 0.0, 4.0]])
+    r = sc.trace_rays(o, d, 1e-4)
+    ids, t, point, normal, uv, ff = (r[k] for k in ("prim_id", "t", "point", "normal", "uv", "front_face"))
+    kinds, mats, centers = sc.prim_table()
+    assert kinds[ids[0]] == 1 and mats[ids[0]] == 1 and centers[ids[0]][2] == 555.0
+    assert t[0] == 250.0
+    np.testing.assert_array_equal(point[0], [100.0, 200.0, 555.0])
+    np.testing.assert_array_equal(normal[0], [0.0, 0.0, -1.0])
+    assert ff[0] == 0
+    np.testing.assert_allclose(uv[0], [100.0 / 555.0, 200.0 / 555.0], rtol=1e-14)
+    sc.close()
+
+
+def test_light_pdf_values_by_hand(wro):
+    """EntityCollection.pdfValue = mean over Scene.lights (entity.zig:371-378) of
+       quad  (entity.zig:503-518): dist^2 / (|cos| * area), dist^2 = t^2 |d|^2, cos = d.n/|d|;
+       sphere (entity.zig:626-644): 1 / (2 pi (1 - sqrt(1 - r^2/|c - o|^2))).
+    Cornell lights (scene.zig:399-406): the glass sphere (190,90,190) r 90 and the light quad start (343,554,332),
+    u = (-150,0,0), v = (0,0,-125): area 18750, plane y = 554.
+    From o = (278, 0, 279.5) straight up, d = (0,1,0): the quad is hit at t = 554 (278 in [193,343], 279.5 in [207,332]),
+    cos = 1 -> pdf_quad = 554^2/18750; the sphere is missed (|x - 190| = 88 but z offset 89.5: 88^2 + 89.5^2 > 90^2) -> 0.
+    From o = (190, 400, 190), d = (0,-1,0): sphere pdf with dist^2 = 310^2; the quad is behind the ray -> 0."""
+    sc = wro.OracleScene("cornell_box")
+    o = np.array([[278.0, 0.0, 279.5], [190.0, 400.0, 190.0]]); d = np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 0.0]])
+    got = sc.light_pdf_values(o, d)
+    want0 = 0.5 * (554.0 ** 2 / 18750.0) + 0.5 * 0.0
+    cos_max = math.sqrt(1.0 - 90.0 ** 2 / 310.0 ** 2)
+    want1 = 0.5 * (1.0 / (2.0 * math.pi * (1.0 - cos_max)))
+    np.testing.assert_allclose(got, [want0, want1], rtol=1e-13)
+    sc.close()
+
+
+# ---- (3) the reference's published render ---------------------------------------------------------------------------------
+def _region_check(rgb8: np.ndarray, tol: float):
+    ref = json.loads((GOLDEN / "cornell_example_regions.json").read_text())
+    cell = ref["cell"]
+    worst = 0.0
+    for r, c in ref["cells"]:
+        got = rgb8[r * cell:(r + 1) * cell, c * cell:(c + 1) * cell].reshape(-1, 3).astype(np.float64).mean(0)
+        want = np.array(ref["grid_mean_rgb8"][r][c])
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst <= tol, f"region means differ from the reference's published render by {worst:.2f} 8-bit levels (> {tol})"
+    return worst
+
+
+def test_cornell_region_means_match_the_references_published_render(wro):
+    """400x400 like the PNG, 48 spp on the host (cell means over 2500 pixels are converged to well under one level), depth 50,
+    quantised by encodeColor (writer.zig:68-94).  Tolerance: 4 of 255 levels per channel per cell; measured worst 3.6
+    (right wall, next to the changed tall box; the left half of the image agrees to 1 level)."""
+    sc = wro.OracleScene("cornell_box")
+    cam = sc.camera(400, 400)
+    p = sc.params(400, 400, 48, 50, seed=7)
+    fb, _ = sc.render(cam, p, wro.RNG_REFERENCE)
+    _region_check(wro.encode_image(fb), 4.0)
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_cornell_region_means_match_the_references_published_render(wro, wrt, ctx):
+    sc = wro.OracleScene("cornell_box")
+    cam = sc.camera(400, 400)
+    p = sc.params(400, 400, 1024, 50, seed=11)
+    ctx.upload_scene(sc.flatten())
+    ctx.render(cam, p)
+    _region_check(ctx.encode_rgb8(400, 400), 4.0)
+    sc.close()
