@@ -81,21 +81,13 @@ def measured_peaks():
 
 
 def scene_images(scene: str):
-    """Texel bytes for image-textured workloads.  The reference assets do not travel to the GPU box; tests/golden holds the
-    reference-decoded wap.jpg, everything else uses the deterministic procedural stand-in (named in `config`)."""
-    import numpy as np
+    """Texel bytes for image-textured workloads: the reference's assets as decoded by the reference's own vendored stb_image
+    (tools/make_texel_fixtures.py; the reference checkout does not travel to the GPU box).  C4's earth.png is full resolution."""
     if scene not in ("earth", "rtw_final", "shrek_quads"):
         return None, None
-    def procedural(name, w, h):
-        yy, xx = np.mgrid[0:h, 0:w]
-        seed = sum(name.encode())
-        r = (xx * 255 // max(w - 1, 1)) ^ ((yy * 7 + seed) & 0xFF)
-        g = (yy * 255 // max(h - 1, 1)) ^ ((xx * 3 + seed * 5) & 0xFF)
-        b = ((xx // 8 + yy // 8) % 2) * 200 + ((xx * yy + seed) % 56)
-        return np.stack([r, g, b], axis=-1).astype(np.uint8)
-    imgs = {"earth.png": procedural("earth.png", 2048, 1024), "wap.jpg": procedural("wap.jpg", 300, 292),
-            "me.jpg": procedural("me.jpg", 2316, 3088)}
-    return imgs, "procedural stand-in texels at the reference assets' resolutions"
+    assets = importlib.import_module("zig-weekend-raytracer_b200.assets")
+    return assets.reference_images(), ("reference assets decoded by the reference's stb_image v2.28 (data/texels; earth.png and "
+                                       "wap.jpg full resolution, me.jpg decimated 4x)")
 
 
 class ClockSampler:

@@ -44,14 +44,12 @@ def ctx(wrt):
 
 
 @pytest.fixture(scope="session")
-def images(wro):
-    """Texel bytes for the image-textured scenes: small procedural stand-ins (the reference assets and
-    /root/reference do not exist on the GPU box); both sides always consume the same bytes."""
-    return {
-        "wap.jpg": wro.procedural_image("wap.jpg", 300, 292),
-        "me.jpg": wro.procedural_image("me.jpg", 231, 308),
-        "earth.png": wro.procedural_image("earth.png", 512, 256),
-    }
+def images():
+    """Texel bytes for the image-textured scenes: the reference's assets decoded by the reference's own vendored stb_image
+    (tools/make_texel_fixtures.py -> zig-weekend-raytracer_b200/data/texels; earth.png and wap.jpg in full, me.jpg decimated
+    4x).  Oracle, host mirror and device always consume the same bytes."""
+    assets = importlib.import_module("zig-weekend-raytracer_b200.assets")
+    return assets.reference_images()
 
 
 def bits(a: np.ndarray) -> np.ndarray:

@@ -5,12 +5,9 @@ The reference (Zig) cannot be executed here, and its tests hold no vectors for t
 ORACLE's outputs (regression guard + the vectors the CUDA path is compared with on the GPU box):
   prim_ids / t_bits : gate-1 dump, primary-ray closest hit of samples [0, n_primary) of every pixel
   radiance          : linear f64 frame of the counter-RNG render (Philox stream shared with the device)
-Image-textured scenes use the procedural stand-in texels of oracle/wro_py.procedural_image (the reference assets do
-not travel to the GPU box).  `assets_*.npz` additionally records checksums of the reference's own assets decoded by
-the reference's vendored stb_image (oracle/_ref/libstbi.so) when /root/reference is mounted.
+Image-textured scenes use the reference's assets as decoded by the reference's vendored stb_image
+(tools/make_texel_fixtures.py -> zig-weekend-raytracer_b200/data/texels; me.jpg decimated 4x).
 """
-import ctypes as C
-import hashlib
 import sys
 from pathlib import Path
 
@@ -34,11 +31,9 @@ CASES = {
 
 
 def main():
-    images = {
-        "wap.jpg": wro.procedural_image("wap.jpg", 300, 292),
-        "me.jpg": wro.procedural_image("me.jpg", 231, 308),
-        "earth.png": wro.procedural_image("earth.png", 512, 256),
-    }
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    images = importlib.import_module("zig-weekend-raytracer_b200.assets").reference_images()
     for name, (w, h, spp, depth, n_primary, scene_seed, n_prims_arg, seed) in CASES.items():
         sc = wro.OracleScene(name, seed=scene_seed, n_prims=n_prims_arg, images=images)
         cam = sc.camera(w, h)
@@ -51,28 +46,6 @@ def main():
                             n_prims=sc.n_prims)
         print(name, "prims", sc.n_prims, "rays", st.rays, "hit fraction", float((ids != 0xFFFFFFFF).mean()))
         sc.close()
-
-    stbi = ROOT / "oracle" / "_ref" / "libstbi.so"
-    assets = Path("/root/reference/assets")
-    if stbi.exists() and assets.exists():
-        lib = C.CDLL(str(stbi))
-        lib.wro_stbi_load.restype = C.POINTER(C.c_ubyte)
-        lib.wro_stbi_load.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        lib.wro_stbi_free.argtypes = [C.POINTER(C.c_ubyte)]
-        out = {}
-        for fn in ["earth.png", "wap.jpg", "me.jpg"]:
-            w, h, c = C.c_int(), C.c_int(), C.c_int()
-            ptr = lib.wro_stbi_load(str(assets / fn).encode(), C.byref(w), C.byref(h), C.byref(c))
-            arr = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, c.value)).copy()
-            lib.wro_stbi_free(ptr)
-            key = fn.replace(".", "_")
-            out[key + "_shape"] = np.array(arr.shape)
-            out[key + "_sha256"] = np.frombuffer(hashlib.sha256(arr.tobytes()).digest(), np.uint8)
-            out[key + "_corner"] = arr[:4, :4].copy()
-            if fn == "wap.jpg":
-                out[key + "_pixels"] = arr  # 300x292x3 = 263 KB raw, compresses well
-            print(fn, arr.shape)
-        np.savez_compressed(HERE / "assets_reference_decode.npz", **out)
 
 
 if __name__ == "__main__":

@@ -58,7 +58,7 @@ def test_flat_scene_is_well_formed(host, images):
     assert kinds.count(4) == 1 and kinds.count(5) == 1            # one Translate(RotateY(...))
     assert kinds.count(3) == 7 + 1023 + 511                        # BVH node counts
     assert f.n_spheres == 1005 and f.n_quads == 2401
-    assert f.n_images == 2 and f.texel_bytes == 300 * 292 * 3 + 231 * 308 * 3
+    assert f.n_images == 2 and f.texel_bytes == 300 * 292 * 3 + 579 * 772 * 3
     assert hs.input_bytes() > f.texel_bytes
     # every collection child index is in range
     for i in range(f.n_entities):

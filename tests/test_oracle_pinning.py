@@ -185,3 +185,33 @@ def test_gpu_cornell_region_means_match_the_references_published_render(wro, wrt
     ctx.render(cam, p)
     _region_check(ctx.encode_rgb8(400, 400), 4.0)
     sc.close()
+
+
+# ---- (4) the texel fixtures are the reference decoder's output --------------------------------------------------------------
+def test_texel_fixtures_are_the_reference_decoders_output(images):
+    """data/texels holds what stb_image v2.28 (the reference's vendored decoder, libs/zstbi) makes of assets/*: the loader
+    checks each blob against the manifest's sha256; where the reference checkout and oracle/_ref/libstbi.so are present
+    (the build container) the full decode is redone and compared with the manifest."""
+    import ctypes as C
+    import hashlib
+    import importlib
+    assets = importlib.import_module("zig-weekend-raytracer_b200.assets")
+    man = assets.manifest()["images"]
+    assert images["earth.png"].shape == (1024, 2048, 3) and images["wap.jpg"].shape == (292, 300, 3)
+    assert man["me.jpg"]["full_shape"] == [3088, 2316, 3]
+    stbi = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libstbi.so"
+    ref_assets = Path("/root/reference/assets")
+    if not (stbi.exists() and ref_assets.exists()):
+        return
+    lib = C.CDLL(str(stbi))
+    lib.wro_stbi_load.restype = C.POINTER(C.c_ubyte)
+    lib.wro_stbi_load.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.wro_stbi_free.argtypes = [C.POINTER(C.c_ubyte)]
+    for name, info in man.items():
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        ptr = lib.wro_stbi_load(str(ref_assets / name).encode(), C.byref(w), C.byref(h), C.byref(c))
+        full = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, c.value)).copy()
+        lib.wro_stbi_free(ptr)
+        assert hashlib.sha256(full.tobytes()).hexdigest() == info["full_sha256"]
+        step = info["decimation"]
+        np.testing.assert_array_equal(full[::step, ::step], images[name])
