@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cull", default="tight", choices=["tight", "reference"])
     ap.add_argument("--spp", type=int, default=0, help="development only: override samples per pixel (marks the line reduced)")
+    ap.add_argument("--res", default="", help="development only: override the frame as WxH (marks the line reduced)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,6 +208,8 @@ def reference_arm(args, wl):
 def main():
     args = parse_args()
     wl = dict(WORKLOADS[args.workload], key=args.workload)
+    if args.res:
+        wl["width"], wl["height"] = (int(v) for v in args.res.lower().split("x"))
     if args.impl == "reference":
         return reference_arm(args, wl)
 
@@ -345,7 +348,7 @@ def main():
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "spp": spp, "depth": depth,
                    "cull": args.cull, "parallelism": f"row-interleaved shards x{n_gpus}" + (" + NCCL gather" if n_gpus > 1 else ""),
                    "l2_policy": "scene is cache-resident by design; per-step traffic is the framebuffer (> L2 only for C5)",
-                   "textures": img_note, "reduced_spp": bool(args.spp)},
+                   "textures": img_note, "reduced_spp": bool(args.spp), "reduced_frame": bool(args.res)},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "rays_per_step": rays_all / args.steps, "paths_per_step": paths_all / args.steps,
         "gather_ms_per_step": gath_ms_max / args.steps,

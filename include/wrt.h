@@ -19,7 +19,9 @@
  *   - all arrays are caller-owned and copied during the call (ownership is one-directional).
  *   - all reals are IEEE-754 binary64 (math.zig:40 `pub const Real = f64`), vectors are xyz triples.
  *   - indices are uint32_t; WRT_NONE means "null pointer / optional absent".
- *   - a wrt_ctx is bound to ONE CUDA device and is thread-compatible (one caller at a time).
+ *   - a wrt_ctx is bound to ONE CUDA device and is thread-compatible (one caller at a time); any number of contexts may
+ *     share a device (every launch carries its own constants as kernel arguments).  Several devices: wrt_group (one
+ *     process) or wrt_comm_init + wrt_render_sharded (one process per device).
  *   - there is no CPU fallback: every entry point that renders fails with WRT_E_CUDA if the device
  *     or the kernels are unavailable.
  */
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WRT_ABI_VERSION 1u
+#define WRT_ABI_VERSION 2u
 #define WRT_NONE 0xFFFFFFFFu
 
 /* status codes */
@@ -68,13 +70,19 @@ enum {
 /* ITexture variants (src/texture.zig:11-16) */
 enum { WRT_TEX_SOLID = 0, WRT_TEX_CHECKER = 1, WRT_TEX_IMAGE = 2 };
 
-/* BVH culling rule used by the device traversal.  Both return the same closest hit
- * whenever the reference's own boxes are conservative; REFERENCE also reproduces the reference
- * when they are not. */
+/* BVH culling rule used by the device traversal.  TIGHT and REFERENCE return the same closest hit
+ * whenever the reference's own boxes are conservative; REFERENCE also reproduces the reference when they are not
+ * (AABB.offset shrinks an instanced box, src/math/aabb.zig:52-60, SURVEY.md A.9-4: scene `rtw_final`).
+ * wrt_upload_scene compares every reference box with the box recomputed from its subtree (x and y, the axes the reference
+ * tests) and counts the ones that do not contain it (wrt_scene_info / wrt_stats .ref_boxes_loose).  The default, AUTO,
+ * is the REFERENCE's RESULT at the best speed: TIGHT when that count is 0, REFERENCE otherwise.  wrt_stats.cull_mode_used
+ * says which one ran. */
 enum {
-    WRT_CULL_TIGHT = 0,     /* 3-axis slab test on boxes recomputed from the primitives (fast path) */
-    WRT_CULL_REFERENCE = 1  /* the reference's test: its cached boxes, x and y only, each axis on its own
+    WRT_CULL_AUTO = 0,      /* default: TIGHT if every reference box contains its subtree, else REFERENCE */
+    WRT_CULL_REFERENCE = 1, /* the reference's test: its cached boxes, x and y only, each axis on its own
                                (src/math/aabb.zig:80-101 + math.zig:186-190) */
+    WRT_CULL_TIGHT = 2      /* 3-axis slab test on boxes recomputed from the primitives (fast path); opt-in where
+                               ref_boxes_loose > 0: returns hits the reference's loose boxes drop */
 };
 
 /* One node of the reference's entity tree (src/entity.zig).  `bbox_*` is the cached AABB.min/max the
@@ -198,6 +206,12 @@ typedef struct wrt_params {
 #define WRT_FLAG_ENGINE_WAVEFRONT 32u  /* force the wavefront engine (path pool + per-material queues in HBM) */
 #define WRT_FLAG_ENGINE_SYNC 64u       /* phase-synchronous megakernel: one 16-warp block per SM, block barriers between phases */
 #define WRT_FLAG_ENGINE_REGROUP 128u   /* phase-synchronous megakernel + per-material regrouping of the block's paths in shared memory */
+#define WRT_FLAG_SHARD_SAMPLES 256u    /* wrt_group_render / wrt_render_sharded: split the sample range instead of the rows */
+/* Sampler upgrade the reference sketches (src/math/sampler.zig:203-247): every random decision of a path (lens, time,
+ * mixture choice, light pick, direction) takes the next Owen-scrambled Sobol dimension (get1D / get2D, dimensions 2, 3, ...
+ * of the pixel sample's Sobol index, wrapping at 1024) instead of the pseudo-random stream.  Changes the estimator's noise,
+ * not its mean; default off (parity mode). */
+#define WRT_FLAG_SAMPLER_SOBOL 512u
 /* Sample chunks: a pixel's samples are summed in order inside a chunk and the chunk sums are added in order, so the
  * chunk count fixes the last bits of the frame.  By default it is chosen from the full frame size, the sample count and
  * the engine (never from the shard or the GPU), so a frame is bit-identical on 1..8 GPUs; WRT_FLAG_CHUNKS(n), n in
@@ -216,8 +230,13 @@ typedef struct wrt_stats {
     uint32_t kernel_launches;/* kernels launched by the last wrt_render* call */
     uint32_t program_ops;    /* size of the compiled traversal program */
     uint32_t n_prims;        /* leaf primitives in DFS order */
-    uint32_t _pad;
+    uint32_t cull_mode_used; /* WRT_CULL_REFERENCE or WRT_CULL_TIGHT: what the last render / gate call resolved AUTO to */
     uint64_t traversal_steps;/* node records + ops visited by the per-lane ordered traversal (0 for the packet scan) */
+    uint32_t ref_boxes_loose;/* bvh_node boxes of the uploaded scene that do not contain their subtree in x / y */
+    uint32_t n_devices;      /* devices that took part in the last render (1 for a plain wrt_ctx) */
+    double gather_ms;        /* device time of the shard gather of the last wrt_group_render (0 otherwise) */
+    double kernel_ms_min;    /* min / max of kernel_ms over the devices of a group (== kernel_ms for one device) */
+    double kernel_ms_max;
 } wrt_stats;
 
 typedef struct wrt_ctx wrt_ctx;
@@ -253,6 +272,8 @@ typedef struct wrt_scene_info {
     uint32_t tree_depth;     /* deepest tree, in records */
     uint32_t max_nesting;    /* stack bound of the ordered traversal */
     uint32_t n_lights;
+    uint32_t ref_boxes_loose;/* bvh_node boxes that do not contain their subtree in x / y (0 => AUTO culling = TIGHT) */
+    uint32_t stack_depth;    /* exact worst-case stack use of the ordered traversal on the rebuilt trees */
 } wrt_scene_info;
 WRT_API int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, char* err, size_t err_cap);
 
@@ -304,6 +325,44 @@ WRT_API int wrt_get_stats(const wrt_ctx* ctx, wrt_stats* out);
 WRT_API int wrt_fp64_issue_peak(wrt_ctx* ctx, double* fma_per_second);
 /* The same probe on the binary32 pipe (the conservative culler runs there). */
 WRT_API int wrt_fp32_issue_peak(wrt_ctx* ctx, double* fma_per_second);
+
+/* Multi-GPU ----------------------------------------------------------------------------------- */
+/* The frame shards like the reference's own job fan-out (src/render.zig:55-73: disjoint row segments, no
+ * synchronisation): device r of n renders image rows r, r+n, r+2n, ... (interleaved for load balance), the shards are
+ * gathered into one device's frame with NCCL point-to-point transfers over NVLink (3 binary64 lanes per pixel on the
+ * wire), and one fused pass writes the caller's framebuffer layout and the RGB8 frame.  Random numbers and Sobol indices
+ * are keyed by the global pixel, and the sample-chunk summation tree by the full frame, so the assembled frame is
+ * bit-identical for every n.  With WRT_FLAG_SHARD_SAMPLES every device renders ALL rows for 1/n of the sample range and the
+ * partial means are added with ncclReduce(ncclSum, ncclDouble) — for small frames at very high sample counts; the sum
+ * order then depends on n (last-bit differences).
+ *
+ * (1) one process, n devices: a wrt_group owns one wrt_ctx per device and an ncclCommInitAll communicator clique. */
+typedef struct wrt_group wrt_group;
+WRT_API int wrt_group_create(const int* device_ids, int n_devices, wrt_group** out);
+WRT_API void wrt_group_destroy(wrt_group* g);
+WRT_API const char* wrt_group_last_error(const wrt_group* g); /* g == NULL: last failed wrt_group_create */
+WRT_API int wrt_group_size(const wrt_group* g);
+/* The context of member i (0 = the root that holds the assembled frame): for wrt_format_ppm, wrt_get_stats, gates. */
+WRT_API wrt_ctx* wrt_group_ctx(wrt_group* g, int i);
+WRT_API int wrt_group_upload_scene(wrt_group* g, const wrt_scene* scene); /* compiled once, copied to every device */
+/* Replaces Renderer.render on n devices; params->row_shard_* are ignored (the group sets them).  `framebuffer` as in
+ * wrt_render; NULL leaves the assembled frame on the root device (wrt_group_encode_rgb8 / wrt_format_ppm read it). */
+WRT_API int wrt_group_render(wrt_group* g, const wrt_camera* cam, const wrt_params* params, void* framebuffer,
+                             size_t pixel_stride_bytes);
+WRT_API int wrt_group_encode_rgb8(wrt_group* g, uint8_t* rgb_out);
+/* Whole-job numbers of the last wrt_group_render: rays/paths summed over the devices, render_ms = max over the devices
+ * + gather, kernel_ms_min/max over the devices, gather_ms, n_devices. */
+WRT_API int wrt_group_get_stats(const wrt_group* g, wrt_stats* out);
+
+/* (2) one process per device (torchrun / MPI): rank 0 makes an id, the caller broadcasts it by its own means, every rank
+ * attaches its context; wrt_render_sharded then renders this rank's shard and gathers to rank 0 inside the library. */
+#define WRT_COMM_ID_BYTES 128
+WRT_API int wrt_comm_unique_id(uint8_t id[WRT_COMM_ID_BYTES]);
+WRT_API int wrt_comm_init(wrt_ctx* ctx, const uint8_t id[WRT_COMM_ID_BYTES], int rank, int n_ranks);
+/* Collective over the ranks of wrt_comm_init.  Rank 0: `framebuffer` = host buffer of the FULL frame, or NULL to leave it
+ * on the device; other ranks: ignored.  params->row_shard_* are ignored (rank / n_ranks are used). */
+WRT_API int wrt_render_sharded(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* framebuffer,
+                               size_t pixel_stride_bytes);
 
 #ifdef __cplusplus
 }

@@ -229,7 +229,7 @@ def test_white_furnace_emissive_background(wro):
     tex[0].kind = 0
     for k in range(3):
         tex[0].color[k] = 1.0
-    flat = abi.Scene(abi_version=1, root=0, lights=0xFFFFFFFF, n_entities=2, n_children=1, n_spheres=1, n_quads=0,
+    flat = abi.Scene(abi_version=abi.WRT_ABI_VERSION, root=0, lights=0xFFFFFFFF, n_entities=2, n_children=1, n_spheres=1, n_quads=0,
                      n_materials=1, n_textures=1, n_images=0, entities=ents, children=children, spheres=sph,
                      materials=mats, textures=tex)
     sc = wro.OracleScene(flat=flat)

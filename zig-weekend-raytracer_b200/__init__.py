@@ -26,6 +26,8 @@ ABI_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_upload_scene", "wrt_render",
     "wrt_render_device", "wrt_encode_rgb8", "wrt_primary_hits", "wrt_trace_rays", "wrt_sobol_pixel_samples",
     "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm", "wrt_check_scene",
+    "wrt_group_create", "wrt_group_destroy", "wrt_group_last_error", "wrt_group_size", "wrt_group_ctx", "wrt_group_upload_scene",
+    "wrt_group_render", "wrt_group_encode_rgb8", "wrt_group_get_stats", "wrt_comm_unique_id", "wrt_comm_init", "wrt_render_sharded",
 ]
 
 
@@ -62,8 +64,23 @@ def _load() -> C.CDLL:
     lib.wrt_fp32_issue_peak.argtypes = [vp, vp]
     lib.wrt_format_ppm.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     lib.wrt_check_scene.argtypes = [vp, vp, C.c_char_p, C.c_size_t]
+    lib.wrt_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.wrt_group_destroy.argtypes = [vp]
+    lib.wrt_group_destroy.restype = None
+    lib.wrt_group_last_error.argtypes = [vp]
+    lib.wrt_group_last_error.restype = C.c_char_p
+    lib.wrt_group_size.argtypes = [vp]
+    lib.wrt_group_ctx.argtypes = [vp, C.c_int]
+    lib.wrt_group_ctx.restype = vp
+    lib.wrt_group_upload_scene.argtypes = [vp, vp]
+    lib.wrt_group_render.argtypes = [vp, vp, vp, vp, C.c_size_t]
+    lib.wrt_group_encode_rgb8.argtypes = [vp, vp]
+    lib.wrt_group_get_stats.argtypes = [vp, vp]
+    lib.wrt_comm_unique_id.argtypes = [vp]
+    lib.wrt_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.wrt_render_sharded.argtypes = [vp, vp, vp, vp, C.c_size_t]
     for name in ABI_SYMBOLS:
-        if name not in ("wrt_destroy", "wrt_last_error", "wrt_abi_version"):
+        if name not in ("wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_group_destroy", "wrt_group_last_error", "wrt_group_ctx"):
             getattr(lib, name).restype = C.c_int
     return lib
 
@@ -88,7 +105,12 @@ def _ptr(a):
 class Context:
     """One wrt_ctx bound to one CUDA device (include/wrt.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed: int | None = None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a member of a Group: the group owns it
+            self._h = C.c_void_p(_borrowed)
+            self.device = device
+            return
         h = C.c_void_p()
         rc = lib.wrt_create(device, C.byref(h))
         if rc != 0:
@@ -98,8 +120,31 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib.wrt_destroy(self._h)
+            if self._owned:
+                lib.wrt_destroy(self._h)
             self._h = None
+
+    # ---- one process per device (include/wrt.h, Multi-GPU (2)) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * WRT_COMM_ID_BYTES)()
+        rc = lib.wrt_comm_unique_id(buf)
+        if rc != 0:
+            raise WrtError(rc, (lib.wrt_group_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        assert len(unique_id) == WRT_COMM_ID_BYTES
+        buf = (C.c_uint8 * WRT_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(lib.wrt_comm_init(self._h, buf, rank, n_ranks))
+
+    def render_sharded(self, cam: Camera, params: Params, out: np.ndarray | None = None, lanes: int = 4):
+        """Collective: every rank renders its shard, rank 0 receives the frame.  `out` (rank 0): host array
+        (height, width, lanes) f64, or None to leave the assembled frame on the device."""
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (params.height, params.width, lanes)
+        self._check(lib.wrt_render_sharded(self._h, C.byref(cam), C.byref(params), _ptr(out), lanes * 8))
+        return out
 
     def __del__(self):
         try:
@@ -181,7 +226,7 @@ class Context:
         self._check(lib.wrt_primary_hits(self._h, C.byref(cam), C.byref(params), n_samples, _ptr(ids), _ptr(t)))
         return ids, t
 
-    def trace_rays(self, origins: np.ndarray, directions: np.ndarray, tmin: float = 1e-4, cull_mode: int = WRT_CULL_TIGHT):
+    def trace_rays(self, origins: np.ndarray, directions: np.ndarray, tmin: float = 1e-4, cull_mode: int = WRT_CULL_AUTO):
         origins = np.ascontiguousarray(origins, dtype=np.float64)
         directions = np.ascontiguousarray(directions, dtype=np.float64)
         n = origins.shape[0]
@@ -211,3 +256,65 @@ class Context:
         out = np.zeros(idx.shape[0], np.float32)
         self._check(lib.wrt_sobol_dimension_samples(self._h, _ptr(idx), _ptr(dim), idx.shape[0], int(owen_fast), seed, _ptr(out)))
         return out
+
+
+class Group:
+    """A wrt_group: one process driving several devices (include/wrt.h, Multi-GPU (1))."""
+
+    def __init__(self, devices):
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = lib.wrt_group_create(arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise WrtError(rc, (lib.wrt_group_last_error(None) or b"").decode())
+        self._h = h
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.wrt_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise WrtError(rc, (lib.wrt_group_last_error(self._h) or b"").decode())
+
+    def __len__(self):
+        return lib.wrt_group_size(self._h)
+
+    def member(self, i: int) -> Context:
+        return Context(self.devices[i], _borrowed=lib.wrt_group_ctx(self._h, i))
+
+    def upload_scene(self, scene: Scene):
+        self._check(lib.wrt_group_upload_scene(self._h, C.byref(scene)))
+
+    def render(self, cam: Camera, params: Params, lanes: int = 4, out: np.ndarray | None = None, to_host: bool = True):
+        if out is None and to_host:
+            out = np.zeros((params.height, params.width, lanes), dtype=np.float64)
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (params.height, params.width, lanes)
+        self._check(lib.wrt_group_render(self._h, C.byref(cam), C.byref(params), _ptr(out), lanes * 8))
+        return out
+
+    def encode_rgb8(self, height: int, width: int) -> np.ndarray:
+        out = np.zeros((height, width, 3), dtype=np.uint8)
+        self._check(lib.wrt_group_encode_rgb8(self._h, _ptr(out)))
+        return out
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(lib.wrt_group_get_stats(self._h, C.byref(s)))
+        return s

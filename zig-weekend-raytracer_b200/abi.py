@@ -7,10 +7,11 @@ from __future__ import annotations
 
 import ctypes as C
 
-WRT_ABI_VERSION = 1
+WRT_ABI_VERSION = 2
 WRT_NONE = 0xFFFFFFFF
-WRT_CULL_TIGHT = 0
+WRT_CULL_AUTO = 0       # default: TIGHT when every reference box contains its subtree, else REFERENCE
 WRT_CULL_REFERENCE = 1
+WRT_CULL_TIGHT = 2
 WRT_FLAG_NO_CLEAR = 1
 WRT_FLAG_DISABLE_DOF = 2
 WRT_FLAG_FORCE_LANE = 4
@@ -19,6 +20,9 @@ WRT_FLAG_ENGINE_MEGAKERNEL = 16
 WRT_FLAG_ENGINE_WAVEFRONT = 32
 WRT_FLAG_ENGINE_SYNC = 64
 WRT_FLAG_ENGINE_REGROUP = 128
+WRT_FLAG_SHARD_SAMPLES = 256
+WRT_FLAG_SAMPLER_SOBOL = 512
+WRT_COMM_ID_BYTES = 128
 
 
 def WRT_FLAG_CHUNKS(n: int) -> int:
@@ -92,10 +96,13 @@ class Params(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [("n_ops", C.c_uint32), ("n_ops_packet", C.c_uint32), ("n_prims", C.c_uint32), ("n_boxes", C.c_uint32),
-                ("n_tree_records", C.c_uint32), ("tree_depth", C.c_uint32), ("max_nesting", C.c_uint32), ("n_lights", C.c_uint32)]
+                ("n_tree_records", C.c_uint32), ("tree_depth", C.c_uint32), ("max_nesting", C.c_uint32), ("n_lights", C.c_uint32),
+                ("ref_boxes_loose", C.c_uint32), ("stack_depth", C.c_uint32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("render_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("kernel_launches", C.c_uint32), ("program_ops", C.c_uint32),
-                ("n_prims", C.c_uint32), ("_pad", C.c_uint32), ("traversal_steps", C.c_uint64)]
+                ("n_prims", C.c_uint32), ("cull_mode_used", C.c_uint32), ("traversal_steps", C.c_uint64),
+                ("ref_boxes_loose", C.c_uint32), ("n_devices", C.c_uint32), ("gather_ms", C.c_double),
+                ("kernel_ms_min", C.c_double), ("kernel_ms_max", C.c_double)]

@@ -42,21 +42,37 @@ def _newer(target: Path, sources) -> bool:
 
 
 def build_wrt(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
-    cu = [CSRC / "wrt_api.cu", CSRC / "wrt_kernels.cu", CSRC / "wrt_program.cu"]
-    deps = cu + [CSRC / "wrt_device.cuh", CSRC / "wrt_kernels.h", CSRC / "wrt_program.h", CSRC / "wrt_sobol_blob.c",
-                 ROOT / "include" / "wrt.h", DATA / "sobol_tables.bin", Path(__file__)]
-    if not force and _newer(LIBWRT, deps):
-        return LIBWRT
+    """Each .cu is compiled to its own object (in parallel, only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    cu = [CSRC / "wrt_api.cu", CSRC / "wrt_kernels.cu", CSRC / "wrt_program.cu", CSRC / "wrt_multi.cu"]
+    hdrs = [CSRC / "wrt_device.cuh", CSRC / "wrt_kernels.h", CSRC / "wrt_program.h", CSRC / "wrt_ctx.h", ROOT / "include" / "wrt.h",
+            Path(__file__)]
+    blob_deps = [CSRC / "wrt_sobol_blob.c", DATA / "sobol_tables.bin", Path(__file__)]
+    objs = [c.with_suffix(".o") for c in cu]
     blob_o = CSRC / "wrt_sobol_blob.o"
+    if extra_flags:
+        force = True
+    if not force and _newer(LIBWRT, cu + hdrs + blob_deps):
+        return LIBWRT
     cc = os.environ.get("CC", "gcc")
-    subprocess.check_call([cc, "-c", "-fPIC", "-O2", f'-DWRT_SOBOL_BLOB="{DATA / "sobol_tables.bin"}"',
-                           str(CSRC / "wrt_sobol_blob.c"), "-o", str(blob_o)])
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-shared", "-o", str(LIBWRT), *map(str, cu), str(blob_o)]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    if force or not _newer(blob_o, blob_deps):
+        subprocess.check_call([cc, "-c", "-fPIC", "-O2", f'-DWRT_SOBOL_BLOB="{DATA / "sobol_tables.bin"}"',
+                               str(CSRC / "wrt_sobol_blob.c"), "-o", str(blob_o)])
+
+    def compile_one(pair):
+        src, obj = pair
+        if not force and _newer(obj, [src] + hdrs):
+            return
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=len(cu)) as pool:
+        list(pool.map(compile_one, zip(cu, objs)))
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIBWRT), *map(str, objs),
+                           str(blob_o), "-ldl", "-Xcompiler", "-pthread"])
     return LIBWRT
 
 

@@ -8,45 +8,25 @@
 #include <string>
 #include <vector>
 
-#include "wrt_device.cuh"
-#include "wrt_kernels.h"
-#include "wrt_program.h"
+#include <nvtx3/nvToolsExt.h>
+
+#include "wrt_ctx.h"
 
 extern "C" const unsigned char wrt_sobol_blob[];
 
+// NVTX ranges around the phases the reference marks with Tracy zones (src/render.zig:30,108,151,195; scene.zig): visible in
+// Nsight Systems / Compute timelines, free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 namespace {
 
+using wrt::DevBuf;
+using wrt::SobolBlob;
+
 thread_local std::string g_create_error;
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;  // capacity in elements
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
-    }
-    cudaError_t ensure(size_t count) {
-        if (count <= n && p) return cudaSuccess;
-        release();
-        if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
-        cudaError_t e = ensure(v.size());
-        if (e != cudaSuccess || v.empty()) return e;
-        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    }
-};
-
-struct SobolBlob {
-    const uint32_t* matrices32;  // [1024*52]
-    const uint64_t* vdc;         // [25][52]
-    const uint64_t* vdc_inv;     // [26][52]
-    uint32_t n_dims, matrix_size, n_vdc, n_vdc_inv;
-};
 
 bool parse_sobol_blob(SobolBlob& b) {
     if (std::memcmp(wrt_sobol_blob, "WRTSOBL1", 8) != 0) return false;
@@ -73,84 +53,18 @@ uint32_t log2u(uint32_t v) {
 
 }  // namespace
 
-struct wrt_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::string err;
-    SobolBlob blob{};
-
-    // scene
-    bool have_scene = false;
-    wrt::CompiledScene cs;
-    wrt::DeviceScene ds{};
-    wrt::DeviceScene ds_pruned{};  // ds with the pruned program (packet scan, WRT_CULL_TIGHT); == ds when nothing was dropped
-    DevBuf<uint4> d_ops;
-    DevBuf<uint4> d_ops_pruned;
-    DevBuf<uint8_t> d_ppm_in, d_ppm_body;
-    DevBuf<uint32_t> d_ppm_blocks;
-    DevBuf<unsigned long long> d_ppm_offsets;
-    DevBuf<wrt::BoxRef> d_boxes_ref;
-    DevBuf<wrt::BoxTight> d_boxes_tight;
-    DevBuf<wrt::Node2> d_nodes2;
-    DevBuf<wrt::SphereGeom> d_spheres;
-    DevBuf<wrt::SphereAux> d_sphere_aux;
-    DevBuf<wrt::QuadGeom> d_quads;
-    DevBuf<wrt::Xform> d_xforms;
-    DevBuf<uint32_t> d_xform_chains;
-    DevBuf<wrt::Material> d_materials;
-    DevBuf<wrt::Texture> d_textures;
-    DevBuf<wrt::ImageDesc> d_images;
-    DevBuf<wrt::Light> d_lights;
-    DevBuf<wrt::BoxTight> d_light_boxes;
-    DevBuf<uint32_t> d_sobol_matrices;
-    DevBuf<wrt::SobolLut> d_sobol_lut;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> texobjs;
-
-    // render state
-    DevBuf<double> d_accum;
-    DevBuf<double> d_fb;
-    DevBuf<uint8_t> d_rgb8;
-    DevBuf<unsigned long long> d_counters;
-    DevBuf<wrt::PathState> d_wf_paths;      // wavefront engine: path pool, queues, counters
-    DevBuf<uint32_t> d_wf_queues;
-    DevBuf<unsigned long long> d_wf_counters;
-    unsigned long long* h_wf_counters = nullptr;  // pinned
-    uint32_t last_pixels = 0;        // pixels of the last render (this shard)
-    bool last_valid = false;
-    uint32_t sobol_w = 0, sobol_h = 0;  // resolution the constant Sobol tables were loaded for
-    wrt::SobolTables sobol_staging{};
-    wrt_stats stats{};
-
-    int fail(int code, const std::string& msg) {
-        err = msg;
-        return code;
-    }
-    int cuda_fail(cudaError_t e, const char* what) {
-        err = std::string(what) + ": " + cudaGetErrorString(e);
-        return WRT_E_CUDA;
-    }
-    void free_images() {
-        for (auto t : texobjs) cudaDestroyTextureObject(t);
-        for (auto a : arrays) cudaFreeArray(a);
-        texobjs.clear();
-        arrays.clear();
-    }
-};
-
 #define CU(call)                                                   \
     do {                                                           \
         cudaError_t e__ = (call);                                  \
         if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); \
     } while (0)
 
-static int bind_device(wrt_ctx* ctx) {
+int wrt::bind_device(wrt_ctx* ctx) {
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "cudaSetDevice");
     return WRT_OK;
 }
+using wrt::bind_device;
 
 extern "C" uint32_t wrt_abi_version(void) { return WRT_ABI_VERSION; }
 
@@ -172,6 +86,8 @@ extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, cha
     info->n_tree_records = (uint32_t)cs.nodes2.size();
     info->max_nesting = cs.max_nesting;
     info->n_lights = (uint32_t)cs.lights.size();
+    info->ref_boxes_loose = cs.ref_boxes_loose;
+    info->stack_depth = cs.stack_depth;
     if (!wrt::check_compiled_scene(cs, info->tree_depth, msg)) { report(msg); return WRT_E_STATE; }
     return WRT_OK;
 }
@@ -222,6 +138,8 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    wrt::comm_release(ctx);
+    ctx->d_shard.release(); ctx->d_staging.release();
     ctx->free_images();
     ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
@@ -251,7 +169,12 @@ static int upload_images(wrt_ctx* ctx, const wrt_scene* sc) {
         const uint64_t need = im.texel_offset + (uint64_t)im.bytes_per_row * im.height;
         if (!sc->texels || need > sc->texel_bytes || im.num_components == 0 || (uint64_t)im.width * im.num_components > im.bytes_per_row)
             return ctx->fail(WRT_E_INVALID, "image texel range out of bounds");
-        std::vector<uchar4> rgba((size_t)im.width * im.height);
+        std::vector<uchar4> rgba;
+        try {
+            rgba.resize((size_t)im.width * im.height);
+        } catch (const std::bad_alloc&) {
+            return ctx->fail(WRT_E_NOMEM, "out of host memory staging an image texture");
+        }
         const uint8_t* base = sc->texels + im.texel_offset;
         const uint64_t total = (uint64_t)im.bytes_per_row * im.height;
         for (uint32_t y = 0; y < im.height; ++y)
@@ -291,19 +214,15 @@ static int upload_images(wrt_ctx* ctx, const wrt_scene* sc) {
     return WRT_OK;
 }
 
-extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
-    if (!ctx) return WRT_E_INVALID;
+int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_scene* scene, double compile_ms) {
+    NvtxRange range("wrt_upload_scene: H2D");
+    auto t0 = std::chrono::steady_clock::now();
     int rc = bind_device(ctx);
     if (rc) return rc;
-    auto t0 = std::chrono::steady_clock::now();
     ctx->have_scene = false;
     ctx->last_valid = false;
-    std::string err;
-    rc = wrt::compile_scene(scene, ctx->cs, err);
-    if (rc != WRT_OK) return ctx->fail(rc, "wrt_upload_scene: " + err);
     rc = upload_images(ctx, scene);
     if (rc != WRT_OK) return rc;
-    wrt::CompiledScene& cs = ctx->cs;
     CU(ctx->d_ops.upload(cs.ops, ctx->stream));
     if (!cs.ops_pruned.empty()) CU(ctx->d_ops_pruned.upload(cs.ops_pruned, ctx->stream));
     CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
@@ -328,23 +247,47 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     ds.n_lights = (uint32_t)cs.lights.size();
     ds.has_lights = cs.has_lights ? 1u : 0u;
     ds.has_moving = cs.has_moving ? 1u : 0u;
-    ds.use_ordered = (cs.max_nesting + 8 <= WRT_STACK_DEPTH) ? 1u : 0u;
+    // ordered traversal only when its exact worst-case stack use fits (ordered_stack_depth walks the rebuilt trees)
+    ds.use_ordered = (cs.stack_depth <= WRT_STACK_DEPTH) ? 1u : 0u;
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
+    ctx->n_ops = cs.ops.size();
+    ctx->has_moving = cs.has_moving;
+    ctx->ref_boxes_loose = cs.ref_boxes_loose;
     ctx->have_scene = true;
     ctx->stats.program_ops = ds.n_ops;
     ctx->stats.n_prims = cs.n_prims;
-    ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->stats.ref_boxes_loose = cs.ref_boxes_loose;
+    ctx->stats.upload_ms = compile_ms + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return WRT_OK;
 }
 
-// Load the constant-memory Sobol tables for a W x H framebuffer (scale = ceilPowerOfTwo(max(W,H)), sampler.zig:188).
+extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
+    if (!ctx) return WRT_E_INVALID;
+    auto t0 = std::chrono::steady_clock::now();
+    ctx->have_scene = false;
+    ctx->last_valid = false;
+    std::string err;
+    wrt::CompiledScene cs;  // host arrays live only for the duration of the upload
+    int rc;
+    {
+        NvtxRange range("wrt_upload_scene: compile");
+        rc = wrt::compile_scene(scene, cs, err);
+    }
+    if (rc != WRT_OK) return ctx->fail(rc, "wrt_upload_scene: " + err);
+    const double compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return wrt::upload_compiled(ctx, cs, scene, compile_ms);
+}
+
+// Build this context's Sobol rows (LaunchParams::sobol) for a W x H framebuffer (scale = ceilPowerOfTwo(max(W,H)), sampler.zig:188).
 static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
     if (ctx->sobol_w == width && ctx->sobol_h == height) return WRT_OK;
     if (width == 0 || height == 0) return ctx->fail(WRT_E_INVALID, "image dimensions must be non-zero");
     const uint32_t mx = width > height ? width : height;
-    if (mx > (1u << 26)) return ctx->fail(WRT_E_LIMIT, "image side exceeds the Sobol table range (2^26)");
-    wrt::SobolTables& t = ctx->sobol_staging;  // staging outlives the async copy; synchronised below
+    // VdCSobolMatrices has 25 rows, VdCSobolMatricesInv 26 (sobolmatrices.zig): resolutions up to 2^25 are addressable
+    if (mx > (1u << 25)) return ctx->fail(WRT_E_LIMIT, "image side exceeds the Sobol table range (2^25)");
+    ctx->sobol_w = ctx->sobol_h = 0;
+    wrt::SobolTables& t = ctx->lp.sobol;
     std::memset(&t, 0, sizeof t);
     t.scale = ceil_pow2(mx);
     t.log2_scale = log2u(t.scale);
@@ -395,10 +338,9 @@ static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
         for (int c = 0; c < 52; ++c) if ((index >> c) & 1) { v0 ^= t.dim0[c]; v1 ^= t.dim1[c]; }
         t.inc0[k] = v0; t.inc1[k] = v1;
     }
-    CU(ctx->d_sobol_lut.upload(lut, ctx->stream));
+    CU(ctx->d_sobol_lut.upload(lut, ctx->stream));  // per-context device memory; ordered on this context's stream
     t.lut = ctx->d_sobol_lut.p;
-    CU(wrt::upload_sobol_tables(t, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `lut` is a local
     ctx->sobol_w = width; ctx->sobol_h = height;
     return WRT_OK;
 }
@@ -407,7 +349,7 @@ static int prepare_sobol(wrt_ctx* ctx, uint32_t width, uint32_t height) {
 static bool use_packet(const wrt_ctx* ctx, uint32_t flags) {
     if (flags & WRT_FLAG_FORCE_LANE) return false;
     if (flags & WRT_FLAG_FORCE_PACKET) return true;
-    return ctx->cs.ops.size() <= WRT_PACKET_MAX_OPS;
+    return ctx->n_ops <= WRT_PACKET_MAX_OPS;
 }
 
 // The scene view a launch scans: the packet traversal under WRT_CULL_TIGHT reads the pruned program (wrt_program.cu,
@@ -430,8 +372,11 @@ static int normalise_params(wrt_ctx* ctx, const wrt_params* in, wrt_params& p) {
     if ((uint64_t)p.width * p.height > 0xFFFFFFFFull) return ctx->fail(WRT_E_LIMIT, "more than 2^32 pixels");
     if (p.samples_per_pixel == 0) return ctx->fail(WRT_E_INVALID, "samples_per_pixel must be non-zero");
     if (p.sample_begin > p.sample_end) return ctx->fail(WRT_E_INVALID, "sample_begin > sample_end");
+    if (p.sample_end > p.samples_per_pixel) return ctx->fail(WRT_E_INVALID, "sample_end > samples_per_pixel");
     if (p.row_shard_index >= p.row_shard_count) return ctx->fail(WRT_E_INVALID, "row_shard_index >= row_shard_count");
-    if (p.cull_mode > WRT_CULL_REFERENCE) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    if (p.cull_mode > WRT_CULL_TIGHT) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    p.cull_mode = (uint32_t)ctx->resolve_cull(p.cull_mode);
+    ctx->stats.cull_mode_used = p.cull_mode;
     return WRT_OK;
 }
 
@@ -449,8 +394,9 @@ static void fill_constants(const wrt_camera& cam, const wrt_params& p, wrt::Rend
 }
 
 // Shared body of wrt_render / wrt_render_device.  `d_out` is a device pointer or NULL (internal buffer + D2H).
-static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* host_fb, void* d_out, size_t stride) {
+int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* host_fb, void* d_out, size_t stride) {
     if (!ctx) return WRT_E_INVALID;
+    NvtxRange range("wrt_render");
     int rc_ = bind_device(ctx);
     if (rc_) return rc_;
     if (!ctx->have_scene) return ctx->fail(WRT_E_STATE, "wrt_render: no scene uploaded");
@@ -463,8 +409,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     rc_ = prepare_sobol(ctx, p.width, p.height);
     if (rc_) return rc_;
 
-    wrt::RenderConstants rc;
+    wrt::RenderConstants& rc = ctx->lp.rc;  // this launch's constants (kernel argument)
     fill_constants(*cam, p, rc);
+    const wrt::LaunchParams& lp = ctx->lp;
     const uint32_t stride_d = (uint32_t)(stride / 8);
     const uint64_t n_pixels64 = (uint64_t)rc.n_rows_local * p.width;
     const uint32_t n_pixels = (uint32_t)n_pixels64;
@@ -479,7 +426,7 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const bool sync_engine = (p.flags & WRT_FLAG_ENGINE_SYNC) != 0;
     // regrouping kernel: packet programs without moving spheres (its staging area carries no ray time)
-    const bool regroup_engine = !sync_engine && (p.flags & WRT_FLAG_ENGINE_REGROUP) && packet && !ctx->cs.has_moving;
+    const bool regroup_engine = !sync_engine && (p.flags & WRT_FLAG_ENGINE_REGROUP) && packet && !ctx->has_moving;
     const bool block_per_sm = sync_engine || regroup_engine;
     const uint32_t grid = block_per_sm ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
@@ -532,7 +479,6 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     }
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(wrt::upload_render_constants(rc, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     uint32_t launches = 0;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -550,14 +496,14 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         A.accum = ctx->d_accum.p; A.capacity = n_slots; A.n_pixels = n_pixels;
         CU(cudaMemsetAsync(A.counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
         const uint32_t wf_grid = (uint32_t)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)ctx->sm_count * 8);
-        CU(wrt::wf_launch_init(A, wf_grid, ctx->stream));
+        CU(wrt::wf_launch_init(lp, A, wf_grid, ctx->stream));
         ++launches;
         // every slot runs chunk_size paths of at most max_depth segments, one segment per iteration
         const uint64_t max_iters = (uint64_t)rc.chunk_size * p.max_ray_bounce_depth + 8;
         const uint32_t check_every = 16;
         bool done = false;
         for (uint64_t it = 0; it < max_iters && !done; ++it) {
-            CU(wrt::wf_launch_iteration(A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
+            CU(wrt::wf_launch_iteration(lp, A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
             launches += 6;
             if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
                 CU(cudaMemcpyAsync(ctx->h_wf_counters, A.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -569,9 +515,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
         wf_rays = ctx->h_wf_counters[8];
         wf_paths = ctx->h_wf_counters[9];
     } else if (rc.total_jobs > 0) {
-        if (regroup_engine) CU(wrt::launch_render_regroup(view, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
-        else if (sync_engine) CU(wrt::launch_render_sync(view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
-        else CU(wrt::launch_render(view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        if (regroup_engine) CU(wrt::launch_render_regroup(lp, view, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        else if (sync_engine) CU(wrt::launch_render_sync(lp, view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
+        else CU(wrt::launch_render(lp, view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -594,6 +540,9 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
     ctx->stats.traversal_steps = wavefront ? 0 : counters[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;
+    ctx->stats.kernel_ms_min = ctx->stats.kernel_ms_max = ms_kernel;
+    ctx->stats.gather_ms = 0.0;
+    ctx->stats.n_devices = 1;
     ctx->stats.kernel_launches = launches;
     ctx->last_pixels = n_pixels;
     ctx->last_valid = true;
@@ -603,14 +552,14 @@ static int render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* pa
 extern "C" int wrt_render(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* framebuffer, size_t pixel_stride_bytes) {
     if (!ctx) return WRT_E_INVALID;
     if (!framebuffer) return ctx->fail(WRT_E_INVALID, "framebuffer is NULL");
-    return render_impl(ctx, cam, params, framebuffer, nullptr, pixel_stride_bytes);
+    return wrt::render_impl(ctx, cam, params, framebuffer, nullptr, pixel_stride_bytes);
 }
 
 extern "C" int wrt_render_device(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* params, void* d_framebuffer,
                                  size_t pixel_stride_bytes) {
     if (!ctx) return WRT_E_INVALID;
     if (!d_framebuffer) return ctx->fail(WRT_E_INVALID, "d_framebuffer is NULL");
-    return render_impl(ctx, cam, params, nullptr, d_framebuffer, pixel_stride_bytes);
+    return wrt::render_impl(ctx, cam, params, nullptr, d_framebuffer, pixel_stride_bytes);
 }
 
 extern "C" int wrt_encode_rgb8(wrt_ctx* ctx, uint8_t* rgb_out) {
@@ -677,7 +626,7 @@ extern "C" int wrt_primary_hits(wrt_ctx* ctx, const wrt_camera* cam, const wrt_p
     if (rc_) return rc_;
     rc_ = prepare_sobol(ctx, p.width, p.height);
     if (rc_) return rc_;
-    wrt::RenderConstants rc;
+    wrt::RenderConstants& rc = ctx->lp.rc;
     fill_constants(*cam, p, rc);
     rc.dof = 0;
     const uint64_t total = (uint64_t)p.width * p.height * n_samples;
@@ -689,9 +638,8 @@ extern "C" int wrt_primary_hits(wrt_ctx* ctx, const wrt_camera* cam, const wrt_p
         cudaError_t e;
         if (prim_ids && (e = d_ids.ensure(total)) != cudaSuccess) { ret = ctx->cuda_fail(e, "cudaMalloc(ids)"); break; }
         if (t && (e = d_t.ensure(total)) != cudaSuccess) { ret = ctx->cuda_fail(e, "cudaMalloc(t)"); break; }
-        if ((e = wrt::upload_render_constants(rc, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "constants"); break; }
         uint32_t grid = (uint32_t)std::min<uint64_t>((total + 127) / 128, (uint64_t)ctx->sm_count * 32);
-        if ((e = wrt::launch_primary_hits(ctx->ds, p.cull_mode, n_samples, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr, grid,
+        if ((e = wrt::launch_primary_hits(ctx->lp, ctx->ds, p.cull_mode, n_samples, prim_ids ? d_ids.p : nullptr, t ? d_t.p : nullptr, grid,
                                           ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "primary_hits_kernel"); break; }
         if (prim_ids && (e = cudaMemcpyAsync(prim_ids, d_ids.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "D2H ids"); break; }
         if (t && (e = cudaMemcpyAsync(t, d_t.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { ret = ctx->cuda_fail(e, "D2H t"); break; }
@@ -712,7 +660,9 @@ extern "C" int wrt_trace_rays(wrt_ctx* ctx, const double* origins, const double*
     if (cull_mode & WRT_TRAV_FORCE_LANE) trav_flags |= WRT_FLAG_FORCE_LANE;
     if (cull_mode & WRT_TRAV_FORCE_PACKET) trav_flags |= WRT_FLAG_FORCE_PACKET;
     cull_mode &= 0xFFu;
-    if (cull_mode > WRT_CULL_REFERENCE) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    if (cull_mode > WRT_CULL_TIGHT) return ctx->fail(WRT_E_INVALID, "unknown cull_mode");
+    cull_mode = (uint32_t)ctx->resolve_cull(cull_mode);
+    ctx->stats.cull_mode_used = cull_mode;
     const bool packet = use_packet(ctx, trav_flags);
     if (n == 0) return WRT_OK;
     if (!origins || !directions) return ctx->fail(WRT_E_INVALID, "origins/directions is NULL");
@@ -770,7 +720,7 @@ extern "C" int wrt_sobol_pixel_samples(wrt_ctx* ctx, uint32_t width, uint32_t he
         TRY(cudaMemcpyAsync(d_c.p, cols, n * 4, cudaMemcpyHostToDevice, ctx->stream));
         TRY(cudaMemcpyAsync(d_r.p, rows, n * 4, cudaMemcpyHostToDevice, ctx->stream));
         TRY(cudaMemcpyAsync(d_s.p, sample_idx, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-        TRY(wrt::launch_sobol_pixel(d_c.p, d_r.p, d_s.p, n, sobol_index ? d_i.p : nullptr, offsets_xy ? d_o.p : nullptr, ctx->stream));
+        TRY(wrt::launch_sobol_pixel(ctx->lp, d_c.p, d_r.p, d_s.p, n, sobol_index ? d_i.p : nullptr, offsets_xy ? d_o.p : nullptr, ctx->stream));
         if (sobol_index) TRY(cudaMemcpyAsync(sobol_index, d_i.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if (offsets_xy) TRY(cudaMemcpyAsync(offsets_xy, d_o.p, 2 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         TRY(cudaStreamSynchronize(ctx->stream));

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/wrt.h"
+#include "wrt_kernels.h"
 
 namespace wrt {
 
@@ -122,6 +123,12 @@ struct SobolTables {               // live part of sobolmatrices.zig for one res
     // Sample s -> s + 1 of one pixel: index and sample bits are GF(2)-linear in (s, pixel), and s ^ (s + 1) = 2^(k+1) - 1
     // with k = number of trailing ones of s, so the bits of dims 0/1 advance by one XOR with inc[k] (built at upload).
     uint32_t inc0[32], inc1[32];
+};
+// What every launch that renders or samples carries as ONE __grid_constant__ argument (1.9 KB of the 4 KB parameter space):
+// the launch's own constant bank, so nothing is shared between contexts, streams or host threads on a device.
+struct LaunchParams {
+    RenderConstants rc;
+    SobolTables sobol;
 };
 
 // ---------------------------------------------------------------------------------------------------------

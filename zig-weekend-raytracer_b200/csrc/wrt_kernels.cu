@@ -19,15 +19,9 @@
 
 namespace wrt {
 
-__constant__ SobolTables c_sobol;
-__constant__ RenderConstants c_rc;
-
-cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream) {
-    return cudaMemcpyToSymbolAsync(c_sobol, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
-}
-cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream) {
-    return cudaMemcpyToSymbolAsync(c_rc, &rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
-}
+// Per-launch constants travel as a __grid_constant__ kernel argument (LaunchParams: RenderConstants + the Sobol rows of
+// the frame's resolution, 1.8 KB): the constant bank of the launch itself, so contexts that share a device — or host
+// threads with a context each — never see one another's tables (there is no module-global __constant__ state).
 
 __device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
@@ -35,11 +29,11 @@ __device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2])
 // rng == nullptr: gate-1 dump (pinhole, time 0).  Draws: block 0 = (lens radius, lens angle), block 1.lo = time.
 __device__ __forceinline__ Ray sample_ray_at(const RenderConstants& rc, uint32_t col, uint32_t row, double ox, double oy, bool dof,
                                              bool need_time, const Rng* rng);
-__device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, bool dof, bool need_time,
-                                          const Rng* rng) {
-    uint64_t idx = sobol_interval_to_index(c_sobol, s, col, row);
+__device__ __forceinline__ Ray sample_ray(const RenderConstants& rc, const SobolTables& sob, uint32_t col, uint32_t row, uint32_t s, bool dof,
+                                          bool need_time, const Rng* rng) {
+    uint64_t idx = sobol_interval_to_index(sob, s, col, row);
     double ox, oy;
-    sobol_pixel_2d(c_sobol, idx, col, row, ox, oy);
+    sobol_pixel_2d(sob, idx, col, row, ox, oy);
     return sample_ray_at(rc, col, row, ox, oy, dof, need_time, rng);
 }
 // The same for a lane that walks the samples of one pixel in order: the Sobol bits of sample s are those of s - 1 advanced
@@ -48,16 +42,16 @@ struct PixelSobol {
     uint32_t v0, v1;
     bool primed;
 };
-__device__ __forceinline__ Ray sample_ray_seq(const RenderConstants& rc, uint32_t col, uint32_t row, uint32_t s, PixelSobol& ps, bool dof,
-                                              bool need_time, const Rng* rng) {
+__device__ __forceinline__ Ray sample_ray_seq(const RenderConstants& rc, const SobolTables& sob, uint32_t col, uint32_t row, uint32_t s,
+                                              PixelSobol& ps, bool dof, bool need_time, const Rng* rng) {
     if (ps.primed) {
-        sobol_pixel_bits_next(c_sobol, s - 1u, ps.v0, ps.v1);
+        sobol_pixel_bits_next(sob, s - 1u, ps.v0, ps.v1);
     } else {
-        sobol_pixel_bits(c_sobol, sobol_interval_to_index(c_sobol, s, col, row), ps.v0, ps.v1);
+        sobol_pixel_bits(sob, sobol_interval_to_index(sob, s, col, row), ps.v0, ps.v1);
         ps.primed = true;
     }
     double ox, oy;
-    sobol_bits_to_offsets(c_sobol, ps.v0, ps.v1, col, row, ox, oy);
+    sobol_bits_to_offsets(sob, ps.v0, ps.v1, col, row, ox, oy);
     return sample_ray_at(rc, col, row, ox, oy, dof, need_time, rng);
 }
 __device__ __forceinline__ Ray sample_ray_at(const RenderConstants& rc, uint32_t col, uint32_t row, double ox, double oy, bool dof,
@@ -263,9 +257,9 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
 enum { TRAV_LANE = 0, TRAV_PACKET = 1 };
 
 template <int CULL, int TRAV>
-__global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_BLOCKS : WRT_RENDER_MIN_BLOCKS) render_kernel(DeviceScene S, double* __restrict__ accum,
+__global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_BLOCKS : WRT_RENDER_MIN_BLOCKS) render_kernel(const __grid_constant__ LaunchParams LP, DeviceScene S, double* __restrict__ accum,
                                                                                          unsigned long long* __restrict__ counters) {
-    const RenderConstants& rc = c_rc;
+    const RenderConstants& rc = LP.rc;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long n_rays = 0, n_paths = 0;
     const double scale = 1.0 / (double)rc.spp;  // pixel_color_scale, render.zig:123
@@ -325,7 +319,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             if (!alive && have_job) {
                 rng.sample = s;
                                 // (the incremental Sobol form of the lane kernel below costs this kernel 2 %: two more live registers at its 80-register cap)
-                ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
+                ray = sample_ray(rc, LP.sobol, col, row, s, dof, need_time, &rng);
                 beta = mk(1, 1, 1);
                 depth_left = rc.max_depth;
                 alive = true;
@@ -390,7 +384,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
             for (;;) {
                 if (!alive && lane_active && s < s_last) {
                     rng.sample = s;
-                    ray = sample_ray_seq(rc, col, row, s, sob, dof, need_time, &rng);
+                    ray = sample_ray_seq(rc, LP.sobol, col, row, s, sob, dof, need_time, &rng);
                     beta = mk(1, 1, 1); L = mk(0, 0, 0);
                     depth_left = rc.max_depth;
                     alive = depth_left > 0;  // depth == 0 returns black (render.zig:199)
@@ -440,9 +434,9 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
 // made instruction fetch the top stall reason of render_kernel (profiles/README.md).  A warp that finishes its job
 // fetches the next one inside the same loop, so the barrier count per warp stays uniform.
 template <int CULL, int TRAV>
-__global__ void __launch_bounds__(WRT_SYNC_BLOCK, 1) render_kernel_sync(DeviceScene S, double* __restrict__ accum,
+__global__ void __launch_bounds__(WRT_SYNC_BLOCK, 1) render_kernel_sync(const __grid_constant__ LaunchParams LP, DeviceScene S, double* __restrict__ accum,
                                                                         unsigned long long* __restrict__ counters) {
-    const RenderConstants& rc = c_rc;
+    const RenderConstants& rc = LP.rc;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long n_rays = 0, n_paths = 0;
     const double scale = 1.0 / (double)rc.spp;
@@ -487,7 +481,7 @@ __global__ void __launch_bounds__(WRT_SYNC_BLOCK, 1) render_kernel_sync(DeviceSc
         }
         if (have_job && !alive && lane_active && s < s_last) {
             rng.sample = s;
-            ray = sample_ray(rc, col, row, s, dof, need_time, &rng);
+            ray = sample_ray(rc, LP.sobol, col, row, s, dof, need_time, &rng);
             beta = mk(1, 1, 1); L = mk(0, 0, 0);
             depth_left = rc.max_depth;
             alive = depth_left > 0;
@@ -552,11 +546,11 @@ struct RegroupSmem {
 };
 
 template <int CULL>
-__global__ void __launch_bounds__(WRT_REGROUP_BLOCK, 1) render_kernel_regroup(DeviceScene S, double* __restrict__ accum,
+__global__ void __launch_bounds__(WRT_REGROUP_BLOCK, 1) render_kernel_regroup(const __grid_constant__ LaunchParams LP, DeviceScene S, double* __restrict__ accum,
                                                                                unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RegroupSmem& sm = *reinterpret_cast<RegroupSmem*>(smem_raw);
-    const RenderConstants& rc = c_rc;
+    const RenderConstants& rc = LP.rc;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t NW = WRT_REGROUP_BLOCK / 32;
     unsigned long long n_rays = 0, n_paths = 0;
@@ -601,7 +595,7 @@ __global__ void __launch_bounds__(WRT_REGROUP_BLOCK, 1) render_kernel_regroup(De
         }
         if (have_job && !alive && lane_active && s < s_last) {
             rng.sample = s;
-            ray = sample_ray(rc, col, row, s, dof, false, &rng);
+            ray = sample_ray(rc, LP.sobol, col, row, s, dof, false, &rng);
             beta = mk(1, 1, 1); L = mk(0, 0, 0);
             depth_left = rc.max_depth;
             alive = depth_left > 0;
@@ -861,14 +855,14 @@ cudaError_t launch_format_ppm(const uint8_t* rgb, uint32_t n_pixels, uint32_t* b
 uint32_t ppm_block_count(uint32_t n_pixels) { return (n_pixels + WRT_PPM_BLOCK_PIXELS - 1) / WRT_PPM_BLOCK_PIXELS; }
 
 template <int CULL>
-__global__ void primary_hits_kernel(DeviceScene S, uint32_t n_samples, uint32_t* __restrict__ ids, double* __restrict__ ts) {
-    const RenderConstants& rc = c_rc;
+__global__ void primary_hits_kernel(const __grid_constant__ LaunchParams LP, DeviceScene S, uint32_t n_samples, uint32_t* __restrict__ ids, double* __restrict__ ts) {
+    const RenderConstants& rc = LP.rc;
     const uint64_t total = (uint64_t)rc.width * rc.height * n_samples;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = (uint32_t)(i % n_samples);
         uint64_t pix = i / n_samples;
         uint32_t col = (uint32_t)(pix % rc.width), row = (uint32_t)(pix / rc.width);
-        Ray r = sample_ray(rc, col, row, s, false, false, nullptr);
+        Ray r = sample_ray(rc, LP.sobol, col, row, s, false, false, nullptr);
         ClosestHit ch = closest_hit_lane<CULL>(S, r.o, r.d, 0.0, 1e-4, CUDART_INF);
         if (ids) ids[i] = (ch.pc == WRT_NONE) ? WRT_NONE : __ldg(&S.ops[ch.pc].w);
         if (ts) ts[i] = (ch.pc == WRT_NONE) ? CUDART_INF : ch.t;
@@ -906,12 +900,12 @@ __global__ void trace_rays_kernel(DeviceScene S, const double* __restrict__ orig
     }
 }
 
-__global__ void sobol_pixel_kernel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+__global__ void sobol_pixel_kernel(const __grid_constant__ LaunchParams LP, const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
                                    double* offsets) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t idx = sobol_interval_to_index(c_sobol, sidx[i], cols[i], rows[i]);
+        uint64_t idx = sobol_interval_to_index(LP.sobol, sidx[i], cols[i], rows[i]);
         if (index_out) index_out[i] = idx;
-        if (offsets) sobol_pixel_2d(c_sobol, idx, cols[i], rows[i], offsets[2 * i], offsets[2 * i + 1]);
+        if (offsets) sobol_pixel_2d(LP.sobol, idx, cols[i], rows[i], offsets[2 * i], offsets[2 * i + 1]);
     }
 }
 
@@ -1012,8 +1006,8 @@ __device__ __forceinline__ bool wf_finish_path(const RenderConstants& rc, const 
 
 // iteration parity selects the extend / regenerate queue pair: kernels of iteration `it` read E[it&1], R[it&1] and write
 // E[(it+1)&1], R[(it+1)&1] (wf_generate appends to E[it&1] before wf_extend drains it).
-__global__ void __launch_bounds__(256) wf_init_kernel(WavefrontArgs A) {
-    const RenderConstants& rc = c_rc;
+__global__ void __launch_bounds__(256) wf_init_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A) {
+    const RenderConstants& rc = LP.rc;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.capacity; slot += gridDim.x * blockDim.x) {
         const uint32_t chunk = slot / A.n_pixels;
         A.paths[slot].sample = rc.sample_begin + chunk * rc.chunk_size;  // first sample of the slot (not yet generated)
@@ -1023,8 +1017,8 @@ __global__ void __launch_bounds__(256) wf_init_kernel(WavefrontArgs A) {
     if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[WQ_REGEN0] = A.capacity;
 }
 
-__global__ void __launch_bounds__(256) wf_generate_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
-    const RenderConstants& rc = c_rc;
+__global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = LP.rc;
     const int q_in = WQ_REGEN0 + (int)parity, q_out = WQ_EXTEND0 + (int)parity;
     const uint32_t n = (uint32_t)A.counters[q_in];
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -1041,7 +1035,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(WavefrontArgs A, Devic
             const uint32_t s = A.paths[slot].sample;
             rng.pixel = row * rc.width + col;
             rng.sample = s;
-            const Ray r = sample_ray(rc, col, row, s, rc.dof != 0, S.has_moving != 0, &rng);
+            const Ray r = sample_ray(rc, LP.sobol, col, row, s, rc.dof != 0, S.has_moving != 0, &rng);
             PathState P;
             P.ox = r.o.x; P.oy = r.o.y; P.oz = r.o.z; P.dx = r.d.x; P.dy = r.d.y; P.dz = r.d.z;
             P.bx = 1.0; P.by = 1.0; P.bz = 1.0; P.lx = 0.0; P.ly = 0.0; P.lz = 0.0;
@@ -1057,8 +1051,8 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(WavefrontArgs A, Devic
 }
 
 template <int CULL, int TRAV>
-__global__ void __launch_bounds__(128) wf_extend_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
-    const RenderConstants& rc = c_rc;
+__global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = LP.rc;
     const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
     const uint32_t n = (uint32_t)A.counters[q_in];
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -1104,8 +1098,8 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(WavefrontArgs A, DeviceS
 }
 
 template <int QUEUE>
-__global__ void __launch_bounds__(128) wf_shade_kernel(WavefrontArgs A, DeviceScene S, uint32_t parity) {
-    const RenderConstants& rc = c_rc;
+__global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = LP.rc;
     const int q_extend = WQ_EXTEND0 + (int)(parity ^ 1u), q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
     const uint32_t n = (uint32_t)A.counters[QUEUE];
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -1159,7 +1153,7 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(WavefrontArgs A, DeviceSc
 }
 
 // reset the queues consumed by iteration `parity` so the next iteration can append to them
-__global__ void wf_reset_kernel(WavefrontArgs A, uint32_t parity) {
+__global__ void wf_reset_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, uint32_t parity) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         A.counters[WQ_EXTEND0 + parity] = 0;
         A.counters[WQ_REGEN0 + parity] = 0;
@@ -1182,31 +1176,31 @@ static cudaError_t dispatch(uint32_t cull_mode, bool packet, F&& f) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
+cudaError_t launch_render(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream) {
     return dispatch(cull_mode, packet, [&](auto c, auto t) {
-        render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(S, accum, counters);
+        render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(lp, S, accum, counters);
     });
 }
-cudaError_t launch_render_regroup(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+cudaError_t launch_render_regroup(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
                                   cudaStream_t stream) {
     const size_t smem = sizeof(RegroupSmem);
     cudaError_t e;
     if (cull_mode == WRT_CULL_REFERENCE) {
         e = cudaFuncSetAttribute(render_kernel_regroup<WRT_CULL_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        render_kernel_regroup<WRT_CULL_REFERENCE><<<grid, WRT_REGROUP_BLOCK, smem, stream>>>(S, accum, counters);
+        render_kernel_regroup<WRT_CULL_REFERENCE><<<grid, WRT_REGROUP_BLOCK, smem, stream>>>(lp, S, accum, counters);
     } else {
         e = cudaFuncSetAttribute(render_kernel_regroup<WRT_CULL_TIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        render_kernel_regroup<WRT_CULL_TIGHT><<<grid, WRT_REGROUP_BLOCK, smem, stream>>>(S, accum, counters);
+        render_kernel_regroup<WRT_CULL_TIGHT><<<grid, WRT_REGROUP_BLOCK, smem, stream>>>(lp, S, accum, counters);
     }
     return cudaGetLastError();
 }
-cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
+cudaError_t launch_render_sync(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
                                unsigned long long* counters, cudaStream_t stream) {
     return dispatch(cull_mode, packet, [&](auto c, auto t) {
-        render_kernel_sync<decltype(c)::value, decltype(t)::value><<<grid, WRT_SYNC_BLOCK, 0, stream>>>(S, accum, counters);
+        render_kernel_sync<decltype(c)::value, decltype(t)::value><<<grid, WRT_SYNC_BLOCK, 0, stream>>>(lp, S, accum, counters);
     });
 }
 cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm) {
@@ -1229,10 +1223,10 @@ cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_
     encode_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(fb, stride_doubles, n_pixels, rgb8);
     return cudaGetLastError();
 }
-cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
+cudaError_t launch_primary_hits(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
                                 cudaStream_t stream) {
-    if (cull_mode == WRT_CULL_REFERENCE) primary_hits_kernel<WRT_CULL_REFERENCE><<<grid, 128, 0, stream>>>(S, n_samples, ids, ts);
-    else primary_hits_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(S, n_samples, ids, ts);
+    if (cull_mode == WRT_CULL_REFERENCE) primary_hits_kernel<WRT_CULL_REFERENCE><<<grid, 128, 0, stream>>>(lp, S, n_samples, ids, ts);
+    else primary_hits_kernel<WRT_CULL_TIGHT><<<grid, 128, 0, stream>>>(lp, S, n_samples, ids, ts);
     return cudaGetLastError();
 }
 cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool packet, const double* origins, const double* dirs, uint64_t n,
@@ -1243,11 +1237,11 @@ cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool pac
                                                                                               uv, front_face);
     });
 }
-cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+cudaError_t launch_sobol_pixel(const LaunchParams& lp, const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
                                double* offsets, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     uint32_t grid = (uint32_t)((n + 127) / 128 < 4096 ? (n + 127) / 128 : 4096);
-    sobol_pixel_kernel<<<grid, 128, 0, stream>>>(cols, rows, sidx, n, index_out, offsets);
+    sobol_pixel_kernel<<<grid, 128, 0, stream>>>(lp, cols, rows, sidx, n, index_out, offsets);
     return cudaGetLastError();
 }
 cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
@@ -1258,21 +1252,21 @@ cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* ind
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_init(const WavefrontArgs& A, uint32_t grid, cudaStream_t stream) {
-    wf_init_kernel<<<grid, 256, 0, stream>>>(A);
+cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint32_t grid, cudaStream_t stream) {
+    wf_init_kernel<<<grid, 256, 0, stream>>>(lp, A);
     return cudaGetLastError();
 }
 // One wavefront iteration: generate -> extend -> shade (surface, metal, other) -> reset of the consumed queues.
-cudaError_t wf_launch_iteration(const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
+cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
                                 uint32_t grid, cudaStream_t stream) {
-    wf_generate_kernel<<<grid, 256, 0, stream>>>(A, S, parity);
+    wf_generate_kernel<<<grid, 256, 0, stream>>>(lp, A, S, parity);
     dispatch(cull_mode, packet, [&](auto c, auto t) {
-        wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(A, S, parity);
+        wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
     });
-    wf_shade_kernel<WQ_SURFACE><<<grid * 2, 128, 0, stream>>>(A, S, parity);
-    wf_shade_kernel<WQ_METAL><<<grid * 2, 128, 0, stream>>>(A, S, parity);
-    wf_shade_kernel<WQ_OTHER><<<grid * 2, 128, 0, stream>>>(A, S, parity);
-    wf_reset_kernel<<<1, 32, 0, stream>>>(A, parity);
+    wf_shade_kernel<WQ_SURFACE><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    wf_shade_kernel<WQ_METAL><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    wf_shade_kernel<WQ_OTHER><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    wf_reset_kernel<<<1, 32, 0, stream>>>(lp, A, parity);
     return cudaGetLastError();
 }
 

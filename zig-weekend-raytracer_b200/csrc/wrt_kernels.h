@@ -61,18 +61,16 @@ struct WavefrontArgs {
     uint32_t n_pixels;            // pixels of this shard (slot % n_pixels = local pixel)
 };
 
-cudaError_t wf_launch_init(const WavefrontArgs& A, uint32_t grid, cudaStream_t stream);
-cudaError_t wf_launch_iteration(const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
+struct LaunchParams;
+cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint32_t grid, cudaStream_t stream);
+cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
                                 uint32_t grid, cudaStream_t stream);
 
-cudaError_t upload_sobol_tables(const SobolTables& t, cudaStream_t stream);
-cudaError_t upload_render_constants(const RenderConstants& rc, cudaStream_t stream);
-
-cudaError_t launch_render(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
+cudaError_t launch_render(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream);
-cudaError_t launch_render_regroup(const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
+cudaError_t launch_render_regroup(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, uint32_t grid, double* accum, unsigned long long* counters,
                                   cudaStream_t stream);
-cudaError_t launch_render_sync(const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
+cudaError_t launch_render_sync(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum,
                                unsigned long long* counters, cudaStream_t stream);
 cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm);
 cudaError_t launch_resolve(const double* accum, uint32_t n_chunks, uint32_t n_pixels, const double clear[3], int no_clear, double* fb,
@@ -82,12 +80,12 @@ cudaError_t launch_encode(const double* fb, uint32_t stride_doubles, uint32_t n_
 cudaError_t launch_format_ppm(const uint8_t* rgb, uint32_t n_pixels, uint32_t* block_bytes, unsigned long long* offsets, uint8_t* body,
                               cudaStream_t stream);
 uint32_t ppm_block_count(uint32_t n_pixels);
-cudaError_t launch_primary_hits(const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
+cudaError_t launch_primary_hits(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, uint32_t n_samples, uint32_t* ids, double* ts, uint32_t grid,
                                 cudaStream_t stream);
 cudaError_t launch_trace_rays(const DeviceScene& S, uint32_t cull_mode, bool packet, const double* origins, const double* dirs, uint64_t n,
                               double tmin, uint32_t* ids, double* ts, double* point, double* normal, double* uv, uint32_t* front_face,
                               uint32_t grid, cudaStream_t stream);
-cudaError_t launch_sobol_pixel(const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
+cudaError_t launch_sobol_pixel(const LaunchParams& lp, const uint32_t* cols, const uint32_t* rows, const uint32_t* sidx, uint64_t n, uint64_t* index_out,
                                double* offsets, cudaStream_t stream);
 cudaError_t launch_sobol_dimension(const uint32_t* matrices, const uint64_t* index, const uint32_t* dimension, uint64_t n,
                                    uint32_t owen_fast, uint32_t seed, float* out, cudaStream_t stream);

@@ -12,6 +12,9 @@
 #include <cstring>
 #include <future>
 #include <limits>
+#include <new>
+#include <stdexcept>
+#include <system_error>
 
 #include "wrt_program.h"
 
@@ -210,6 +213,12 @@ struct Compiler {
             case WRT_ENT_BVH_NODE: {
                 Box3 tb;
                 if (!tight_box(id, tb)) { ok = false; break; }
+                // Does the reference's cached box contain its subtree on the two axes its AABB.hit tests (aabb.zig:80-101)?
+                // AABB.offset (aabb.zig:52-60) and RotateY's box (entity.zig:139,143) can make it smaller: the reference
+                // then drops hits a conservative culler keeps, and WRT_CULL_AUTO must use the reference's test.
+                if (tb.valid() && !(e.bbox_min[0] <= tb.mn[0] && e.bbox_min[1] <= tb.mn[1] && e.bbox_max[0] >= tb.mx[0] &&
+                                    e.bbox_max[1] >= tb.mx[1]))
+                    ++out.ref_boxes_loose;
                 const uint32_t box = push_box(e, tb);
                 const size_t at = out.ops.size();
                 out.ops.push_back(make_uint4(OP_NODE, box, 0, 0));
@@ -509,11 +518,21 @@ struct Compiler {
         out.nodes2[rec] = n;
         uint32_t depth_l = 0, depth_r = 0;
         const bool fork = level <= 4 && child_rec[0] != WRT_NONE && child_rec[1] != WRT_NONE && (mid - lo) >= 8192 && (hi - mid) >= 8192;
+        bool forked = false;
         if (fork) {
-            auto left = std::async(std::launch::async, [&] { return build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]); });
-            depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
-            depth_l = left.get();
-        } else {
+            std::future<uint32_t> left;
+            try {
+                left = std::async(std::launch::async, [&] { return build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]); });
+                forked = true;
+            } catch (const std::system_error&) {  // no thread to be had: build this level serially
+                forked = false;
+            }
+            if (forked) {
+                depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
+                depth_l = left.get();
+            }
+        }
+        if (!forked) {
             if (child_rec[0] != WRT_NONE) depth_l = build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]);
             if (child_rec[1] != WRT_NONE) depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
         }
@@ -763,10 +782,57 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
     return true;
 }
 
+namespace {
+uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi);
+uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard) {
+    if (rec >= cs.nodes2.size() || guard > 4096) return 1u << 20;  // malformed: never fits
+    const Node2& r = cs.nodes2[rec];
+    uint32_t need = 0;
+    const uint32_t desc[2] = {r.l_desc, r.r_desc}, end[2] = {r.l_end, r.r_end};
+    for (int k = 0; k < 2; ++k) {
+        if (desc[k] == WRT_NONE) continue;
+        const uint32_t c = (desc[k] & 0x80000000u) ? stack_need_record(cs, desc[k] & 0x7FFFFFFFu, guard + 1) : stack_need_range(cs, desc[k], end[k]);
+        need = std::max(need, c);
+    }
+    const bool two = r.l_desc != WRT_NONE && r.r_desc != WRT_NONE;
+    return need + (two ? 1u : 0u);  // the other child waits on the stack while this one is descended
+}
+uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi) {
+    uint32_t need = 0;
+    for (uint32_t pc = lo; pc < hi && pc < cs.ops.size();) {
+        const uint4 op = cs.ops[pc];
+        if (op.x == OP_NODE) {  // nested tree: the rest of the range waits while it is descended
+            need = std::max(need, 1u + stack_need_record(cs, op.y, 0));
+            pc = op.z > pc ? op.z : pc + 1;
+        } else {
+            ++pc;
+        }
+    }
+    return need;
+}
+}  // namespace
+
+uint32_t ordered_stack_depth(const CompiledScene& cs) {
+    if (cs.ops.empty()) return 0;
+    return stack_need_range(cs, 0, (uint32_t)cs.ops.size() - 1);
+}
+
 int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err) {
-    out = CompiledScene();
-    Compiler c(scene, out, err);
-    return c.run();
+    // nothing may unwind through the C ABI (a Zig or C caller): allocation failures of the vectors and std::system_error of
+    // the concurrent SAH build come back as codes
+    try {
+        out = CompiledScene();
+        Compiler c(scene, out, err);
+        const int rc = c.run();
+        if (rc == WRT_OK) out.stack_depth = ordered_stack_depth(out);
+        return rc;
+    } catch (const std::bad_alloc&) {
+        err = "out of host memory while compiling the scene";
+        return WRT_E_NOMEM;
+    } catch (const std::exception& e) {
+        err = std::string("scene compilation failed: ") + e.what();
+        return WRT_E_INVALID;
+    }
 }
 
 }  // namespace wrt

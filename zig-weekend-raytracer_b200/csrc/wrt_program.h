@@ -27,12 +27,19 @@ struct CompiledScene {
     uint32_t n_prims = 0;
     uint32_t max_xform_depth = 0;
     uint32_t max_nesting = 0;  // deepest chain of bvh_node / instance ops
+    uint32_t stack_depth = 0;  // exact worst-case stack use of the ordered traversal over nodes2 (ordered_stack_depth)
+    uint32_t ref_boxes_loose = 0;  // bvh_node boxes of the reference that do not contain their subtree's box in x / y
     bool has_lights = false;
     bool has_moving = false;
 };
 
 // Returns WRT_OK or a WRT_E_* code with `err` set.
 int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err);
+
+// Worst-case number of live stack entries of closest_hit_ordered (wrt_device.cuh) over this scene's trees: a child-pair
+// record defers at most one child while it descends the other, a bvh_node met inside a leaf range defers the rest of the
+// range.  The traversal is only used when this fits WRT_STACK_DEPTH.
+uint32_t ordered_stack_depth(const CompiledScene& cs);
 
 // Structural self-check of a compiled scene (host only; wrt_check_scene, tests/test_program.py): skip links, transform
 // nesting, the packet program against the full one, and that every ordered-traversal tree reaches each primitive op of

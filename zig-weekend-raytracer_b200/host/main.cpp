@@ -4,7 +4,7 @@
 //   --image_width=<usize> (required)   --image_height=<usize> (required)   --image_out_path=image.ppm
 //   --thread_pool_size=8 (PPM writer threads only; rays are traced on the GPU)   --scene=emissive
 //   --samples_per_pixel=10   --ray_bounce_max_depth=20
-// Additions (non-breaking): --device=0  --seed=<u64>  --cull=tight|reference  --asset_dir=assets/  --synthetic_prims=N
+// Additions (non-breaking): --device=0  --devices=0,1,..  --shard=rows|samples  --seed=<u64>  --cull=auto|tight|reference  --asset_dir=assets/  --synthetic_prims=N
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -42,8 +42,11 @@ struct UserArgs {  // main.zig:20-28 (+ additions)
     size_t samples_per_pixel = 10;
     size_t ray_bounce_max_depth = 20;
     int device = 0;
+    std::vector<int> devices;  // --devices=0,1,2,...: one process, several GPUs (wrt_group); empty = {device}
+    bool shard_samples = false; // --shard=samples: split the sample range over the devices instead of the rows
+    bool sampler_sobol = false; // --sampler=sobol: Owen-scrambled Sobol dimensions for every path decision (sampler.zig:203-247)
     uint64_t seed = 1;
-    uint32_t cull = WRT_CULL_TIGHT;
+    uint32_t cull = WRT_CULL_AUTO;
     std::string asset_dir = "assets/";
     uint32_t synthetic_prims = 1u << 20;
     bool writer_on_device = false;  // --writer=device: wrt_format_ppm instead of the host thread pool
@@ -55,7 +58,7 @@ void printUsage(FILE* out) {  // argparser.zig:94-113
     std::fprintf(out, "\t--thread_pool_size=<usize>\n\t--scene=<scene.SceneType>\n");
     for (const auto& n : wrh::sceneTypeNames()) std::fprintf(out, "\t\t%s\n", n.c_str());
     std::fprintf(out, "\t--samples_per_pixel=<usize>\n\t--ray_bounce_max_depth=<usize>\n");
-    std::fprintf(out, "\t--device=<i32>\n\t--seed=<u64>\n\t--cull=<tight|reference>\n\t--asset_dir=<[]const u8>\n\t--synthetic_prims=<u32>\n\t--writer=<host|device>\n");
+    std::fprintf(out, "\t--device=<i32>\n\t--devices=<i32,i32,...>\n\t--shard=<rows|samples>\n\t--sampler=<random|sobol>\n\t--seed=<u64>\n\t--cull=<auto|tight|reference>\n\t--asset_dir=<[]const u8>\n\t--synthetic_prims=<u32>\n\t--writer=<host|device>\n");
 }
 
 bool parseUnsigned(const std::string& v, unsigned long long& out) {  // std.fmt.parseInt(.., 10)
@@ -76,7 +79,8 @@ bool parseUnsigned(const std::string& v, unsigned long long& out) {  // std.fmt.
 // cacheArgVal + parse (argparser.zig:64-136): any number of leading '-', key=value, help / h, unknown keys rejected.
 UserArgs parseUserArgs(int argc, char** argv) {
     static const char* known[] = {"image_width", "image_height", "image_out_path", "thread_pool_size", "scene", "samples_per_pixel",
-                                  "ray_bounce_max_depth", "device", "seed", "cull", "asset_dir", "synthetic_prims", "writer"};
+                                  "ray_bounce_max_depth", "device", "devices", "shard", "sampler", "seed", "cull", "asset_dir", "synthetic_prims",
+                                  "writer"};
     std::map<std::string, std::string> cache;
     for (int a = 1; a < argc; ++a) {
         std::string arg = argv[a];
@@ -121,8 +125,32 @@ UserArgs parseUserArgs(int argc, char** argv) {
         else if (cache["writer"] == "host") args.writer_on_device = false;
         else throw ParseArgsError::ParseEnumFailed;
     }
+    if (cache.count("devices")) {
+        std::string list = cache["devices"];
+        size_t pos = 0;
+        while (pos <= list.size()) {
+            const size_t comma = list.find(',', pos);
+            const std::string item = list.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+            unsigned long long v = 0;
+            if (!parseUnsigned(item, v)) throw ParseArgsError::ParseIntFailed;
+            args.devices.push_back(static_cast<int>(v));
+            if (comma == std::string::npos) break;
+            pos = comma + 1;
+        }
+    }
+    if (cache.count("shard")) {
+        if (cache["shard"] == "samples") args.shard_samples = true;
+        else if (cache["shard"] == "rows") args.shard_samples = false;
+        else throw ParseArgsError::ParseEnumFailed;
+    }
+    if (cache.count("sampler")) {
+        if (cache["sampler"] == "sobol") args.sampler_sobol = true;
+        else if (cache["sampler"] == "random") args.sampler_sobol = false;
+        else throw ParseArgsError::ParseEnumFailed;
+    }
     if (cache.count("cull")) {
         if (cache["cull"] == "tight") args.cull = WRT_CULL_TIGHT;
+        else if (cache["cull"] == "auto") args.cull = WRT_CULL_AUTO;
         else if (cache["cull"] == "reference") args.cull = WRT_CULL_REFERENCE;
         else throw ParseArgsError::ParseEnumFailed;
     }
@@ -155,7 +183,8 @@ int main(int argc, char** argv) {
     }
     try {
         wrh::ThreadPool thread_pool(args.thread_pool_size);
-        wrh::Backend backend(args.device);  // fails loudly without a CUDA device
+        if (args.devices.empty()) args.devices.push_back(args.device);
+        wrh::Backend backend(args.devices);  // fails loudly without a CUDA device
 
         wrh::Renderer renderer;  // main.zig:77-83
         renderer.thread_pool = &thread_pool;
@@ -166,6 +195,7 @@ int main(int argc, char** argv) {
         renderer.backend = &backend;
         renderer.seed = args.seed;
         renderer.cull_mode = args.cull;
+        renderer.flags = (args.shard_samples ? WRT_FLAG_SHARD_SAMPLES : 0u) | (args.sampler_sobol ? WRT_FLAG_SAMPLER_SOBOL : 0u);
 
         wrh::Framebuffer framebuffer = wrh::Framebuffer::init(args.image_height, args.image_width);
 
@@ -185,6 +215,10 @@ int main(int argc, char** argv) {
                      static_cast<unsigned long long>(renderer.last_stats.paths), static_cast<unsigned long long>(renderer.last_stats.rays),
                      renderer.last_stats.kernel_ms, renderer.last_stats.render_ms,
                      renderer.last_stats.kernel_ms > 0 ? renderer.last_stats.rays / renderer.last_stats.kernel_ms / 1e3 : 0.0);
+        std::fprintf(stderr, "info: %u device(s), kernel min/max %.3f / %.3f ms, gather %.3f ms, culling %s (%u loose reference boxes)\n",
+                     renderer.last_stats.n_devices, renderer.last_stats.kernel_ms_min, renderer.last_stats.kernel_ms_max,
+                     renderer.last_stats.gather_ms, renderer.last_stats.cull_mode_used == WRT_CULL_REFERENCE ? "reference" : "tight",
+                     renderer.last_stats.ref_boxes_loose);
 
         wrh::WriterPPM writer;  // main.zig:100-104
         writer.thread_pool = &thread_pool;

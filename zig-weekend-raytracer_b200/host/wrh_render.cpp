@@ -164,19 +164,20 @@ uint64_t FlatScene::inputBytes() const {
 }
 
 // ---- back end ----------------------------------------------------------------------------------------------------
-Backend::Backend(int cuda_device) {
-    const int rc = wrt_create(cuda_device, &ctx_);
-    if (rc != WRT_OK) throw std::runtime_error(std::string("wrt_create failed: ") + wrt_last_error(nullptr));
+Backend::Backend(int cuda_device) : Backend(std::vector<int>{cuda_device}) {}
+Backend::Backend(const std::vector<int>& cuda_devices) {
+    const int rc = wrt_group_create(cuda_devices.data(), static_cast<int>(cuda_devices.size()), &group_);
+    if (rc != WRT_OK) throw std::runtime_error(std::string("wrt_group_create failed: ") + wrt_group_last_error(nullptr));
 }
-Backend::~Backend() { wrt_destroy(ctx_); }
+Backend::~Backend() { wrt_group_destroy(group_); }
 
 void Renderer::render(const Camera& camera, const IEntity& entity, Framebuffer& framebuffer) {  // render.zig:29
     if (!backend) throw std::runtime_error("Renderer.render: no CUDA back end attached (there is no CPU fallback)");
-    wrt_ctx* ctx = backend->ctx();
+    wrt_group* group = backend->group();
     FlatScene flat;
     flattenScene(entity, light_entities, flat);
-    if (wrt_upload_scene(ctx, &flat.view) != WRT_OK)
-        throw std::runtime_error(std::string("wrt_upload_scene: ") + wrt_last_error(ctx));
+    if (wrt_group_upload_scene(group, &flat.view) != WRT_OK)
+        throw std::runtime_error(std::string("wrt_group_upload_scene: ") + wrt_group_last_error(group));
 
     const wrt_camera cam = camera.view(framebuffer.num_cols, framebuffer.num_rows);  // camera.getViewport, render.zig:47
     wrt_params p{};
@@ -191,16 +192,24 @@ void Renderer::render(const Camera& camera, const IEntity& entity, Framebuffer& 
     p.row_shard_index = 0;
     p.row_shard_count = 1;
     p.cull_mode = cull_mode;
-    // framebuffer.clear(clear_color) + the job fan-out + `buffer[..] += color` all happen on the device
-    if (wrt_render(ctx, &cam, &p, framebuffer.buffer.data(), framebuffer.pixelStrideBytes()) != WRT_OK)
-        throw std::runtime_error(std::string("wrt_render: ") + wrt_last_error(ctx));
+    p.flags = flags;
+    // framebuffer.clear(clear_color) + the job fan-out over the devices + `buffer[..] += color` + the gather all happen on the
+    // device side (render.zig:33, 55-73)
+    if (wrt_group_render(group, &cam, &p, framebuffer.buffer.data(), framebuffer.pixelStrideBytes()) != WRT_OK)
+        throw std::runtime_error(std::string("wrt_group_render: ") + wrt_group_last_error(group));
     wrt_stats st{};
-    wrt_get_stats(ctx, &st);
+    wrt_group_get_stats(group, &st);
     last_stats.paths = st.paths;
     last_stats.rays = st.rays;
     last_stats.render_ms = st.render_ms;
     last_stats.kernel_ms = st.kernel_ms;
     last_stats.upload_ms = st.upload_ms;
+    last_stats.gather_ms = st.gather_ms;
+    last_stats.kernel_ms_min = st.kernel_ms_min;
+    last_stats.kernel_ms_max = st.kernel_ms_max;
+    last_stats.n_devices = st.n_devices;
+    last_stats.cull_mode_used = st.cull_mode_used;
+    last_stats.ref_boxes_loose = st.ref_boxes_loose;
 }
 
 }  // namespace wrh

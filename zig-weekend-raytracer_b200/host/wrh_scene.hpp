@@ -167,19 +167,25 @@ class ThreadPool;  // wrh_writer.hpp
 struct RenderStats {
     uint64_t paths = 0, rays = 0;
     double render_ms = 0, kernel_ms = 0, upload_ms = 0;
+    double gather_ms = 0, kernel_ms_min = 0, kernel_ms_max = 0;
+    uint32_t n_devices = 1, cull_mode_used = 0, ref_boxes_loose = 0;
 };
 
-// Owns the wrt_ctx of one CUDA device.  No CPU fallback: construction throws when the device is unavailable.
+// Owns the device side: a wrt_group over one or more CUDA devices (include/wrt.h, Multi-GPU (1)).  No CPU fallback:
+// construction throws when a device is unavailable.
 class Backend {
    public:
     explicit Backend(int cuda_device = 0);
+    explicit Backend(const std::vector<int>& cuda_devices);
     ~Backend();
     Backend(const Backend&) = delete;
     Backend& operator=(const Backend&) = delete;
-    wrt_ctx* ctx() const { return ctx_; }
+    wrt_ctx* ctx() const { return wrt_group_ctx(group_, 0); }  // the root: holds the assembled frame
+    wrt_group* group() const { return group_; }
+    int size() const { return wrt_group_size(group_); }
 
    private:
-    wrt_ctx* ctx_ = nullptr;
+    wrt_group* group_ = nullptr;
 };
 
 struct Renderer {  // render.zig:19-27
@@ -192,7 +198,8 @@ struct Renderer {  // render.zig:19-27
     // back end (additions)
     Backend* backend = nullptr;
     uint64_t seed = 0;
-    uint32_t cull_mode = WRT_CULL_TIGHT;
+    uint32_t cull_mode = WRT_CULL_AUTO;  // the reference's result at the best speed (include/wrt.h)
+    uint32_t flags = 0;                  // WRT_FLAG_* (e.g. WRT_FLAG_SHARD_SAMPLES, WRT_FLAG_SAMPLER_SOBOL)
     RenderStats last_stats;
 
     // render.zig:29: throws std::runtime_error carrying wrt_last_error on failure (the reference's `!void`)
