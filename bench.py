@@ -61,7 +61,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="wrt", choices=["wrt", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cull", default="tight", choices=["tight", "reference"])
+    ap.add_argument("--cull", default="auto", choices=["auto", "tight", "reference"])
+    ap.add_argument("--shard", default="rows", choices=["rows", "samples"], help="N > 1: what the devices split")
+    ap.add_argument("--no-all-workloads", dest="all_workloads", action="store_false",
+                    help="skip the short runs of the other BASELINE configs after the headline timing")
     ap.add_argument("--spp", type=int, default=0, help="development only: override samples per pixel (marks the line reduced)")
     ap.add_argument("--res", default="", help="development only: override the frame as WxH (marks the line reduced)")
     ap.add_argument("--seed", type=int, default=1)
@@ -157,7 +160,32 @@ def cpu_sample_spp(wl, override):
     return {"C1": 16, "C2": 16, "C3": 4, "C4": 8, "C5": 1}[wl["key"]]
 
 
-def run_cpu(wl, spp_sample, seed, threads=None):
+CPU_FLAGS = {"libwro.so": "-O2 -ffp-contract=off -fno-fast-math (portable build, the one the parity tests load)",
+             "libwro_native.so": "-O3 -march=native -ffp-contract=off -fno-fast-math (built on this host)"}
+
+
+def native_oracle():
+    """oracle/libwro_native.so, built ON this host (so -march=native is this host's ISA); None when it cannot be built."""
+    try:
+        subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "libwro_native.so"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=300)
+        lib = ROOT / "oracle" / "libwro_native.so"
+        return lib if lib.exists() else None
+    except Exception:
+        return None
+
+
+def run_cpu(wl, spp_sample, seed, threads=None, lib=None):
+    """One bounded CPU render of the workload with the oracle (the checker, timed here as the CPU baseline only).  `lib`
+    selects the build; it runs in a child process because the binding loads one library per process."""
+    if lib is not None:
+        code = ("import json,sys; sys.path.insert(0, %r); import bench; wl = json.loads(sys.argv[1]); "
+                "print(json.dumps(bench.run_cpu(wl, int(sys.argv[2]), int(sys.argv[3]))))" % str(ROOT))
+        out = subprocess.run([sys.executable, "-c", code, json.dumps(wl), str(spp_sample), str(seed)], capture_output=True, text=True,
+                             env=dict(os.environ, WRO_LIB=str(lib)), timeout=1800)
+        if out.returncode != 0:
+            raise RuntimeError("CPU leg failed: " + out.stderr[-400:])
+        return tuple(json.loads(out.stdout.strip().splitlines()[-1]))
     sys.path.insert(0, str(ROOT / "oracle"))
     import wro_py as wro  # the checker, timed here as the CPU baseline only
     imgs, _ = scene_images(wl["scene"])
@@ -167,7 +195,30 @@ def run_cpu(wl, spp_sample, seed, threads=None):
     threads = threads or wro.host_threads()
     _, st = sc.render(cam, p, wro.RNG_REFERENCE, threads=threads)
     sc.close()
-    return st.rays, st.paths, st.seconds, threads
+    return int(st.rays), int(st.paths), float(st.seconds), int(threads)
+
+
+def cpu_baseline_record(wl, spp_sample, seed, W, H, depth):
+    """The CPU number reported beside the GPU one: the faster of the two builds of the oracle, both stated with their flags."""
+    wl_cpu = dict(wl, n_prims=1 << 14) if wl["key"] == "C5" else wl
+    builds = {}
+    native = native_oracle()
+    for name, lib in (("libwro_native.so", native), ("libwro.so", ROOT / "oracle" / "libwro.so")):
+        if lib is None:
+            continue
+        try:
+            r, _, s_, thr = run_cpu(wl_cpu, spp_sample, seed, lib=lib)
+            builds[name] = {"value": r / s_ / 1e6, "seconds": s_, "cores": thr, "flags": CPU_FLAGS[name]}
+        except Exception as e:  # the portable build always exists; a failed native build is only noted
+            builds[name] = {"error": str(e)[:200]}
+    ok = {k: v for k, v in builds.items() if "value" in v}
+    best = max(ok, key=lambda k: ok[k]["value"])
+    return {"value": ok[best]["value"], "unit": UNIT, "cores": ok[best]["cores"], "kind": "port", "build": best,
+            "flags": ok[best]["flags"], "seconds": ok[best]["seconds"],
+            "sample": f"{spp_sample} of {wl['spp']} spp per pixel over the full {W}x{H} frame, depth {depth}"
+                      + (", 2^14 of 2^20 primitives" if wl["key"] == "C5" else ""),
+            "builds": builds,
+            "note": "throughput is spp-independent; a full-spp CPU frame time quoted from it is an extrapolation"}
 
 
 def reference_arm(args, wl):
@@ -179,12 +230,14 @@ def reference_arm(args, wl):
         wl = dict(wl, n_prims=1 << 14)  # the reference's culling visits every leaf (aabb.zig:80-101): bound the sample
     sample = (f"{spp_sample} of {wl['spp']} spp per pixel over the full {wl['width']}x{wl['height']} frame, depth {wl['depth']}"
               + (", 2^14 of 2^20 primitives" if wl["key"] == "C5" else ""))
+    native = native_oracle()
+    lib = native or (ROOT / "oracle" / "libwro.so")
     for _ in range(args.warmup):
-        run_cpu(wl, max(1, spp_sample // 4), args.seed)
+        run_cpu(wl, max(1, spp_sample // 4), args.seed, lib=lib)
     rays = secs = 0.0
     threads = 0
     for _ in range(args.steps):
-        r, _, s, threads = run_cpu(wl, spp_sample, args.seed)
+        r, _, s, threads = run_cpu(wl, spp_sample, args.seed, lib=lib)
         rays += r; secs += s
     value = rays / secs / 1e6
     line = {
@@ -193,7 +246,8 @@ def reference_arm(args, wl):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": wl["width"], "height": wl["height"], "spp": wl["spp"],
                    "depth": wl["depth"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "build": lib.name,
+                         "flags": CPU_FLAGS[lib.name]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU port of the reference algorithm (oracle/, same job decomposition and culling); the Zig reference "
                 "cannot be built in this image (no Zig toolchain)",
@@ -205,6 +259,36 @@ def reference_arm(args, wl):
 # ---------------------------------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------------------------------
+def measure_workload(wrt, host, ctx, key, spp_override, seed, steps, warmup):
+    """One short device-resident measurement of another BASELINE config on this GPU (the `workloads` sub-record)."""
+    import torch
+    wl = dict(WORKLOADS[key], key=key)
+    spp = spp_override or wl["spp"]
+    imgs, _ = scene_images(wl["scene"])
+    scene = host.HostScene(wl["scene"], seed=1, synthetic_prims=wl.get("n_prims", 0), images=imgs)
+    ctx.upload_scene(scene.flat())
+    up_ms = ctx.stats().upload_ms
+    W, H = wl["width"], wl["height"]
+    cam = scene.camera(W, H)
+    params = scene.params(W, H, spp, wl["depth"], seed=seed, cull_mode=wrt.WRT_CULL_AUTO)
+    d_fb = torch.zeros((H, W, 4), dtype=torch.float64, device=f"cuda:{ctx.device}")
+    for _ in range(warmup):
+        ctx.render_device(cam, params, d_fb.data_ptr(), 32)
+    rays = ms = kms = 0.0
+    for _ in range(steps):
+        ctx.render_device(cam, params, d_fb.data_ptr(), 32)
+        st = ctx.stats()
+        rays += st.rays; ms += st.render_ms; kms += st.kernel_ms
+    hbm_peak, _ = measured_peaks()
+    rec = {"workload": wl["name"], "spp": spp, "reduced_spp": spp != wl["spp"], "steps": steps, "warmup": warmup,
+           "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps, "rays_per_step": rays / steps,
+           "upload_ms": up_ms, "traversal": "packet" if ctx.stats().program_ops <= 96 else "ordered, per lane",
+           "roofline_hbm_frac": (rays / (kms * 1e-3)) * wl["b_ray"] / 1e9 / hbm_peak,
+           "algorithmic_bytes_per_ray": wl["b_ray"], "algorithmic_fp64_instr_per_ray": wl["f_ray"]}
+    scene.close() if hasattr(scene, "close") else None
+    return rec
+
+
 def main():
     args = parse_args()
     wl = dict(WORKLOADS[args.workload], key=args.workload)
@@ -235,20 +319,23 @@ def main():
 
     spp = args.spp or wl["spp"]
     W, H, depth = wl["width"], wl["height"], wl["depth"]
-    cull = wrt.WRT_CULL_TIGHT if args.cull == "tight" else wrt.WRT_CULL_REFERENCE
+    cull = {"auto": wrt.WRT_CULL_AUTO, "tight": wrt.WRT_CULL_TIGHT, "reference": wrt.WRT_CULL_REFERENCE}[args.cull]
+    flags = wrt.WRT_FLAG_SHARD_SAMPLES if args.shard == "samples" else 0
     imgs, img_note = scene_images(wl["scene"])
     scene = host.HostScene(wl["scene"], seed=1, synthetic_prims=wl.get("n_prims", 0), images=imgs)
     flat = scene.flat()
     cam = scene.camera(W, H)
     ctx = wrt.Context(local)
     ctx.upload_scene(flat)
-    params = scene.params(W, H, spp, depth, seed=args.seed, cull_mode=cull, row_shard_index=rank, row_shard_count=world)
-    rows_local = ctx.local_rows(params)
-    rows_pad = (H + world - 1) // world
     LANES = 4
-    d_fb = torch.zeros((rows_pad, W, LANES), dtype=torch.float64, device=f"cuda:{local}")
-    gather_list = [torch.zeros_like(d_fb) for _ in range(world)] if (world > 1 and rank == 0) else None
-    d_full = torch.zeros((H, W, LANES), dtype=torch.float64, device=f"cuda:{local}") if rank == 0 else None
+    if dist:
+        # multi-GPU goes through the library's own boundary (include/wrt.h, Multi-GPU (2)): rank 0 makes the NCCL id, torch
+        # only carries it to the other ranks; the shard gather runs inside wrt_render_sharded
+        box = [wrt.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+    params = scene.params(W, H, spp, depth, seed=args.seed, cull_mode=cull, flags=flags)
+    d_fb = torch.zeros((H, W, LANES), dtype=torch.float64, device=f"cuda:{local}") if not dist else None
     h_fb = torch.zeros((H, W, LANES), dtype=torch.float64).pin_memory() if rank == 0 else None
 
     def barrier():
@@ -257,22 +344,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    distributed = importlib.import_module("zig-weekend-raytracer_b200.distributed")
-
-    def gather_frame():
-        """NCCL gather of the row shards to rank 0 + interleave into the full frame (N > 1 only)."""
-        if dist:
-            distributed.gather_frame(dist, d_fb, H, rank, world, out=d_full, gather_list=gather_list)
-
     def device_step():
-        ctx.render_device(cam, params, d_fb.data_ptr(), LANES * 8)
-        st = ctx.stats()
-        g_ms = 0.0
+        """Scene resident, frame left in HBM (rank 0's for N > 1: shards rendered, gathered and assembled on the device)."""
         if dist:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); gather_frame(); e1.record(); torch.cuda.synchronize()
-            g_ms = e0.elapsed_time(e1)
-        return st.rays, st.paths, st.render_ms, st.kernel_ms, g_ms, st.kernel_launches
+            ctx.render_sharded(cam, params, out=None)
+        else:
+            ctx.render_device(cam, params, d_fb.data_ptr(), LANES * 8)
+        st = ctx.stats()
+        return st.rays, st.paths, st.render_ms, st.kernel_ms, st.gather_ms, st.kernel_launches
 
     fp64_peak = ctx.fp64_issue_peak() if rank == 0 else 0.0
     fp32_peak = ctx.fp32_issue_peak() if rank == 0 else 0.0
@@ -298,9 +377,14 @@ def main():
     # whole-job aggregate: sum of rays over ranks / max time over ranks
     t = torch.tensor([dev_ms, kern_ms, wall_ms, gath_ms], dtype=torch.float64, device=f"cuda:{local}")
     c = torch.tensor([rays, paths, launches], dtype=torch.float64, device=f"cuda:{local}")
+    k_all = [torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
     if dist:
+        dist.all_gather(k_all, torch.tensor([kern_ms / args.steps], dtype=torch.float64, device=f"cuda:{local}"))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    else:
+        k_all[0][0] = kern_ms / args.steps
+    kernel_ms_per_rank = [float(k.item()) for k in k_all]
     dev_ms_max, kern_ms_max, wall_ms_max, gath_ms_max = t.tolist()
     rays_all, paths_all, launches_all = c.tolist()
     value = rays_all / (dev_ms_max * 1e-3) / 1e6
@@ -312,14 +396,10 @@ def main():
     for _ in range(args.steps):
         ctx.upload_scene(flat)  # H2D of the scene arrays (the step's inputs)
         if dist:
-            ctx.render_device(cam, params, d_fb.data_ptr(), LANES * 8)
-            e2e_rays += ctx.stats().rays
-            gather_frame()
-            if rank == 0:
-                h_fb.copy_(d_full, non_blocking=False)
+            ctx.render_sharded(cam, params, out=h_fb.numpy() if rank == 0 else None)  # gather + D2H of the full frame on rank 0
         else:
             ctx.render(cam, params, lanes=LANES, out=h_fb.numpy())  # D2H into the pinned host framebuffer
-            e2e_rays += ctx.stats().rays
+        e2e_rays += ctx.stats().rays
     barrier()
     e2e_s = time.perf_counter() - t0
     e = torch.tensor([e2e_rays], dtype=torch.float64, device=f"cuda:{local}")
@@ -328,11 +408,13 @@ def main():
         dist.all_reduce(e, op=dist.ReduceOp.SUM)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     e2e_value = e.item() / ts.item() / 1e6
-    h2d = scene.input_bytes() + 256 + 136  # scene arrays + camera + params structs
-    d2h = H * W * LANES * 8 + 32           # framebuffer + ray counters
+    h2d = (scene.input_bytes() + 256 + 136) * n_gpus  # scene arrays + camera + params structs, to every device
+    d2h = H * W * LANES * 8 + 32 * n_gpus            # framebuffer (rank 0) + ray counters
+    stats0 = ctx.stats()
 
     if rank != 0:
         if dist:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
@@ -341,42 +423,57 @@ def main():
     rays_per_s_kernel = rays_all / (kern_ms_max * 1e-3)
     ach_gbs = rays_per_s_kernel * wl["b_ray"] / 1e9 / n_gpus  # per GPU, the kernel alone
     ach_issue = rays_per_s_kernel * wl["f_ray"] / n_gpus
+    cache_resident = wl["key"] != "C5"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "spp": spp, "depth": depth,
-                   "cull": args.cull, "parallelism": f"row-interleaved shards x{n_gpus}" + (" + NCCL gather" if n_gpus > 1 else ""),
+                   "cull": args.cull + (" -> " + ("reference" if stats0.cull_mode_used == wrt.WRT_CULL_REFERENCE else "tight")),
+                   "parallelism": (f"{'sample-range' if args.shard == 'samples' else 'row-interleaved'} shards x{n_gpus}"
+                                   + (" + NCCL gather inside wrt_render_sharded" if n_gpus > 1 else "")),
                    "l2_policy": "scene is cache-resident by design; per-step traffic is the framebuffer (> L2 only for C5)",
                    "textures": img_note, "reduced_spp": bool(args.spp), "reduced_frame": bool(args.res)},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "rays_per_step": rays_all / args.steps, "paths_per_step": paths_all / args.steps,
         "gather_ms_per_step": gath_ms_max / args.steps,
+        "kernel_ms_per_rank": {"min": min(kernel_ms_per_rank), "max": max(kernel_ms_per_rank), "all": kernel_ms_per_rank},
         "mean_radiance": mean,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": (wl["dram_b_per_ray_ncu"] * rays_all / args.steps) if "dram_b_per_ray_ncu" in wl else None,
-                     "traffic_unit": "bytes per launch (ncu DRAM bytes per ray at 64 spp x rays of this launch)",
-                     "algorithmic_bytes_per_launch": wl["b_ray"] * rays_all / args.steps,
+                     "traffic": (wl["dram_b_per_ray_ncu"] * rays_all / args.steps / n_gpus) if "dram_b_per_ray_ncu" in wl else None,
+                     "traffic_unit": "bytes per launch (ncu DRAM bytes per ray x rays of this launch; source in profiles/README.md)",
+                     "algorithmic_bytes_per_launch": wl["b_ray"] * rays_all / args.steps / n_gpus,
                      "kernel": "render_kernel", "kernel_ms_per_launch": kern_ms_max / args.steps,
                      "algorithmic_bytes_per_ray": wl["b_ray"], "peak_source": peak_src,
-                     "note": "cache-resident scene: HBM is not the binding bound here, see roofline_issue"},
+                     "note": ("NOMINAL for this workload: the scene is cache-resident (real DRAM traffic is `traffic`, a fraction of a "
+                              "percent of the algorithmic bytes), so this is not achieved HBM bandwidth; the binding bound is "
+                              "roofline_issue") if cache_resident else
+                             "2^20 primitives: node / primitive fetches miss L1 and contend in L2; HBM is the bound to report"},
         "roofline_issue": {"bound": "fp64_issue", "achieved": ach_issue / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64 instr/s",
                            "frac": (ach_issue / fp64_peak) if fp64_peak else None, "algorithmic_fp64_instr_per_ray": wl["f_ray"],
                            "peak_source": "DFMA micro-kernel measured live (wrt_fp64_issue_peak)",
                            "fp32_issue_peak": fp32_peak / 1e9, "fp32_note": "FFMA micro-kernel (wrt_fp32_issue_peak): the pipe the box tests run on"},
     }
     if not args.no_cpu_baseline and n_gpus == 1:
-        spp_s = cpu_sample_spp(wl, args.cpu_sample_spp)
-        wl_cpu = dict(wl, n_prims=1 << 14) if wl["key"] == "C5" else wl
-        r, _, s, thr = run_cpu(wl_cpu, spp_s, args.seed)
-        line["cpu_baseline"] = {"value": r / s / 1e6, "unit": UNIT, "cores": thr, "kind": "port",
-                                "sample": f"{spp_s} of {wl['spp']} spp per pixel over the full {W}x{H} frame, depth {depth}"
-                                          + (", 2^14 of 2^20 primitives" if wl["key"] == "C5" else ""), "seconds": s}
+        line["cpu_baseline"] = cpu_baseline_record(wl, cpu_sample_spp(wl, args.cpu_sample_spp), args.seed, W, H, depth)
+    if args.all_workloads and n_gpus == 1 and not args.spp and not args.res:
+        # the other BASELINE configs, measured by whoever runs this command (short: 1 warm-up + 2 steps each; C5 at reduced spp,
+        # its full-spp campaign is in profiles/)
+        others = {}
+        for key, spp_o in (("C1", 0), ("C3", 0), ("C4", 0), ("C5", 16)):
+            if key == wl["key"]:
+                continue
+            try:
+                others[key] = measure_workload(wrt, host, ctx, key, spp_o, args.seed, steps=2, warmup=1)
+            except Exception as ex:  # a sub-record must never lose the headline
+                others[key] = {"error": str(ex)[:200]}
+        line["workloads"] = others
     print(json.dumps(line))
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -16,7 +16,8 @@ import numpy as np
 
 ORACLE_DIR = Path(__file__).resolve().parent
 ROOT = ORACLE_DIR.parent
-LIB_PATH = ORACLE_DIR / "libwro.so"
+# WRO_LIB=<file> selects another build of the same sources (bench.py: libwro_native.so, -O3 -march=native on the GPU box's host)
+LIB_PATH = Path(os.environ["WRO_LIB"]) if os.environ.get("WRO_LIB") else ORACLE_DIR / "libwro.so"
 
 _spec = importlib.util.spec_from_file_location("wrt_abi", ROOT / "zig-weekend-raytracer_b200" / "abi.py")
 abi = importlib.util.module_from_spec(_spec)

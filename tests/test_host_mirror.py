@@ -155,3 +155,28 @@ def test_cli_fails_loudly_without_a_gpu(host, tmp_path):
     assert r.returncode == 1
     assert "no CPU fallback" in r.stderr
     assert not (tmp_path / "x.ppm").exists()
+
+
+def test_host_loader_decodes_the_reference_assets_like_zstbi(host, images):
+    """Image.initFromFile (image.zig:12-17): the host library carries the reference's vendored stb_image, compiled where it
+    lies, so `--asset_dir=<reference>/assets/` loads the JPEG / PNG files themselves.  Where the reference checkout is
+    mounted (the build container) the texels the loader hands to wrt_upload_scene must equal the committed reference decode;
+    a missing image is an error, as in the reference (no stand-in)."""
+    import ctypes as C
+    from pathlib import Path
+    with pytest.raises(ValueError, match="ImageInitFailed"):
+        host.HostScene("earth", seed=1, asset_dir="/nonexistent/")
+    assets = Path("/root/reference/assets")
+    if not assets.exists():
+        pytest.skip("reference checkout not mounted")
+    hs = host.HostScene("earth", seed=1, asset_dir=str(assets) + "/")
+    f = hs.flat()
+    assert f.n_images == 1 and f.images[0].width == 2048 and f.images[0].height == 1024 and f.images[0].num_components == 3
+    texels = np.ctypeslib.as_array(C.cast(f.texels, C.POINTER(C.c_uint8)), shape=(f.texel_bytes,))
+    np.testing.assert_array_equal(texels.reshape(1024, 2048, 3), images["earth.png"])
+    hs.close()
+    hs = host.HostScene("shrek_quads", seed=1, asset_dir=str(assets) + "/")
+    f = hs.flat()
+    texels = np.ctypeslib.as_array(C.cast(f.texels, C.POINTER(C.c_uint8)), shape=(f.texel_bytes,))
+    np.testing.assert_array_equal(texels.reshape(292, 300, 3), images["wap.jpg"])
+    hs.close()

@@ -85,14 +85,22 @@ HOST_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibi
 def build_host(force: bool = False) -> Path:
     """Host-side mirror of the reference interface (scene construction, flattening, Renderer.render, PPM writer) as
     libwrth.so, plus the `weekend-raytracer` command line driver.  Both link libwrt.so through $ORIGIN."""
-    lib_srcs = [HOST / n for n in ("wrh_entity.cpp", "wrh_scenes.cpp", "wrh_render.cpp", "wrh_writer.cpp", "wrh_capi.cpp")]
+    lib_srcs = [HOST / n for n in ("wrh_entity.cpp", "wrh_scenes.cpp", "wrh_render.cpp", "wrh_writer.cpp", "wrh_image.cpp", "wrh_capi.cpp")]
     hdrs = [HOST / n for n in ("wrh_math.hpp", "wrh_rng.hpp", "wrh_scene.hpp", "wrh_writer.hpp")] + [ROOT / "include" / "wrt.h"]
     cxx = os.environ.get("CXX", "g++")
     link = [f"-L{PKG}", "-lwrt", "-Wl,-rpath,$ORIGIN"]
+    # JPEG / PNG decode = the reference's vendored stb_image.h, compiled where it lies in the reference checkout (never copied)
+    stbi_flags = []
+    for cand in (os.environ.get("WRT_STBI_INCLUDE"), "/root/reference/libs/zstbi/libs/stbi"):
+        if cand and (Path(cand) / "stb_image.h").exists():
+            stbi_flags = ["-DWRH_HAVE_STBI", f"-I{cand}"]
+            break
+    if not stbi_flags and LIBWRTH.exists() and CLI.exists() and not force:
+        return LIBWRTH  # no header here (e.g. the GPU box): keep the artefacts built where the reference checkout was
     if force or not _newer(LIBWRTH, lib_srcs + hdrs + [LIBWRT, Path(__file__)]):
-        subprocess.check_call([cxx, *HOST_FLAGS, "-shared", "-o", str(LIBWRTH), *map(str, lib_srcs), *link])
+        subprocess.check_call([cxx, *HOST_FLAGS, *stbi_flags, "-shared", "-o", str(LIBWRTH), *map(str, lib_srcs), *link])
     if force or not _newer(CLI, lib_srcs + hdrs + [HOST / "main.cpp", LIBWRT, Path(__file__)]):
-        subprocess.check_call([cxx, *HOST_FLAGS, "-o", str(CLI), str(HOST / "main.cpp"),
+        subprocess.check_call([cxx, *HOST_FLAGS, *stbi_flags, "-o", str(CLI), str(HOST / "main.cpp"),
                                *map(str, lib_srcs[:-1]), *link])
     return LIBWRTH
 

@@ -19,24 +19,6 @@ Image Image::fromPixels(uint32_t w, uint32_t h, uint32_t comps, const uint8_t* p
     return im;
 }
 
-// Deterministic RGB pattern standing in for an asset that is not present (same formula as the test helper).
-Image Image::procedural(const std::string& name, uint32_t w, uint32_t h) {
-    Image im;
-    im.width = w; im.height = h; im.num_components = 3; im.bytes_per_row = w * 3;
-    im.data.resize(static_cast<size_t>(im.bytes_per_row) * h);
-    long seed = 0;
-    for (unsigned char c : name) seed += c;
-    for (long y = 0; y < static_cast<long>(h); ++y)
-        for (long x = 0; x < static_cast<long>(w); ++x) {
-            const long r = (x * 255 / std::max<long>(w - 1, 1)) ^ ((y * 7 + seed) & 0xFF);
-            const long g = (y * 255 / std::max<long>(h - 1, 1)) ^ ((x * 3 + seed * 5) & 0xFF);
-            const long b = ((x / 8 + y / 8) % 2) * 200 + ((x * y + seed) % 56);
-            uint8_t* px = &im.data[static_cast<size_t>(y) * im.bytes_per_row + static_cast<size_t>(x) * 3];
-            px[0] = static_cast<uint8_t>(r); px[1] = static_cast<uint8_t>(g); px[2] = static_cast<uint8_t>(b);
-        }
-    return im;
-}
-
 bool Image::loadPnm(const std::string& path, Image& out) {
     std::ifstream f(path, std::ios::binary);
     if (!f) return false;

@@ -27,8 +27,10 @@ struct Image {  // image.zig:7-48 over zstbi.Image
     uint32_t width = 0, height = 0, num_components = 0, bytes_per_row = 0;
     std::vector<uint8_t> data;  // empty => the reference's "no image" state (magenta)
     static Image fromPixels(uint32_t w, uint32_t h, uint32_t comps, const uint8_t* px);
-    static Image procedural(const std::string& name, uint32_t w, uint32_t h);  // stand-in when an asset is absent
     static bool loadPnm(const std::string& path, Image& out);                   // binary P6 / P5
+    // Image.initFromFile (image.zig:12-17): JPEG / PNG through the reference's vendored stb_image (wrh_image.cpp)
+    static bool loadFromFile(const std::string& path, Image& out, std::string& why);
+    static bool decoderAvailable();
 };
 
 enum class TextureKind : uint32_t { solid_color = WRT_TEX_SOLID, checkerboard = WRT_TEX_CHECKER, image = WRT_TEX_IMAGE };

@@ -21,18 +21,17 @@ struct Builder {
     const ITexture* tex(ITexture t) { s.textures.push_back(t); return &s.textures.back(); }
     const IMaterial* mat(IMaterial m) { s.materials.push_back(m); return &s.materials.back(); }
 
-    // ImageTexture.initTextureFromPath (texture.zig:38-42): caller-supplied pixels, else <asset_dir>/<stem>.ppm,
-    // else a procedural stand-in (the build image has no JPEG/PNG decoder of its own; see tools/assets_to_ppm.py).
+    // ImageTexture.initTextureFromPath (texture.zig:38-42): caller-supplied pixels, else <asset_dir>/<file> decoded like
+    // zstbi does (wrh_image.cpp), else a pre-converted <asset_dir>/<stem>.ppm.  A missing / undecodable image is an error, as
+    // in the reference (`try img.Image.initFromFile`): there is no stand-in.
     const ITexture* imageTexture(const std::string& file) {
         for (const auto& kv : ctx.images)
             if (kv.first == file) { s.images.push_back(kv.second); return tex(ImageTexture::initTexture(&s.images.back())); }
         Image im;
+        std::string why;
         const std::string stem = file.substr(0, file.find_last_of('.'));
-        if (!Image::loadPnm(ctx.asset_dir + stem + ".ppm", im)) {
-            std::fprintf(stderr, "warning: %s%s.ppm not found; using a procedural stand-in for %s\n", ctx.asset_dir.c_str(),
-                         stem.c_str(), file.c_str());
-            im = Image::procedural(file, 512, 256);
-        }
+        if (!Image::loadFromFile(ctx.asset_dir + file, im, why) && !Image::loadPnm(ctx.asset_dir + stem + ".ppm", im))
+            throw std::runtime_error("ImageInitFailed: " + why);
         s.images.push_back(std::move(im));
         return tex(ImageTexture::initTexture(&s.images.back()));
     }
