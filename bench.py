@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--impl", default="wrt", choices=["wrt", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cull", default="auto", choices=["auto", "tight", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "megakernel", "wavefront"], help="development: force an engine")
     ap.add_argument("--shard", default="rows", choices=["rows", "samples"], help="N > 1: what the devices split")
     ap.add_argument("--no-all-workloads", dest="all_workloads", action="store_false",
                     help="skip the short runs of the other BASELINE configs after the headline timing")
@@ -321,6 +322,7 @@ def main():
     W, H, depth = wl["width"], wl["height"], wl["depth"]
     cull = {"auto": wrt.WRT_CULL_AUTO, "tight": wrt.WRT_CULL_TIGHT, "reference": wrt.WRT_CULL_REFERENCE}[args.cull]
     flags = wrt.WRT_FLAG_SHARD_SAMPLES if args.shard == "samples" else 0
+    flags |= {"auto": 0, "megakernel": wrt.WRT_FLAG_ENGINE_MEGAKERNEL, "wavefront": wrt.WRT_FLAG_ENGINE_WAVEFRONT}[args.engine]
     imgs, img_note = scene_images(wl["scene"])
     scene = host.HostScene(wl["scene"], seed=1, synthetic_prims=wl.get("n_prims", 0), images=imgs)
     flat = scene.flat()
@@ -429,7 +431,7 @@ def main():
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "spp": spp, "depth": depth,
-                   "cull": args.cull + (" -> " + ("reference" if stats0.cull_mode_used == wrt.WRT_CULL_REFERENCE else "tight")),
+                   "engine": args.engine, "cull": args.cull + (" -> " + ("reference" if stats0.cull_mode_used == wrt.WRT_CULL_REFERENCE else "tight")),
                    "parallelism": (f"{'sample-range' if args.shard == 'samples' else 'row-interleaved'} shards x{n_gpus}"
                                    + (" + NCCL gather inside wrt_render_sharded" if n_gpus > 1 else "")),
                    "l2_policy": "scene is cache-resident by design; per-step traffic is the framebuffer (> L2 only for C5)",

@@ -461,6 +461,23 @@ def test_wavefront_engine_is_bit_identical_to_megakernel(ctx, wrt, wro, images, 
     sc.close()
 
 
+def test_wavefront_ordered_extend_on_the_synthetic_scene(ctx, wrt, wro):
+    """The persistent extend kernel of the wavefront engine (per-lane ray replacement, ordered traversal) against the
+    megakernel on a scene with deep SAH trees and 64 lights: bit-identical frames, ray and path counts."""
+    sc = wro.OracleScene("synthetic", seed=1, n_prims=8192)
+    ctx.upload_scene(sc.flatten())
+    w, h = 96, 54
+    cam = sc.camera(w, h)
+    chunks = wrt.WRT_FLAG_CHUNKS(2)
+    a = ctx.render(cam, sc.params(w, h, 8, 20, seed=5, flags=wrt.WRT_FLAG_ENGINE_MEGAKERNEL | chunks))
+    sa = ctx.stats()
+    b = ctx.render(cam, sc.params(w, h, 8, 20, seed=5, flags=wrt.WRT_FLAG_ENGINE_WAVEFRONT | chunks))
+    sb = ctx.stats()
+    np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert (sa.rays, sa.paths) == (sb.rays, sb.paths) and sb.traversal_steps > 0
+    sc.close()
+
+
 @pytest.mark.parametrize("name", ["cornell_box", "balls", "rtw_final", "synthetic"])
 def test_packet_and_lane_traversals_agree(ctx, wrt, wro, images, name):
     """The warp-uniform packet scan and the per-lane scan are the same sequential closest-hit search: forcing either on

@@ -434,7 +434,10 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     // wavefront (queues in HBM, one small kernel per stage) without its state traffic; the wavefront is selected by flag.
     bool wavefront = false;
     if (p.flags & WRT_FLAG_ENGINE_MEGAKERNEL) wavefront = false;
-    if ((p.flags & WRT_FLAG_ENGINE_WAVEFRONT) && p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0) wavefront = true;
+    // the Sobol-dimension sampler lives in the wavefront kernels only (the megakernels sit at their register caps)
+    const bool sobol_sampler = (p.flags & WRT_FLAG_SAMPLER_SOBOL) != 0;
+    if ((p.flags & (WRT_FLAG_ENGINE_WAVEFRONT | WRT_FLAG_SAMPLER_SOBOL)) && p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0) wavefront = true;
+    if (sobol_sampler && !wavefront) return ctx->fail(WRT_E_INVALID, "WRT_FLAG_SAMPLER_SOBOL needs depth > 0 and a non-empty frame / sample range");
     // Sample chunks (include/wrt.h, WRT_FLAG_CHUNKS): a function of the FULL frame, the sample count and the engine only —
     // not of the shard or the grid — so the per-pixel summation tree, and with it every bit of the frame, is the same on
     // 1 or 8 GPUs.  The accumulators (chunks x shard pixels x 24 B) stay under 0.8 GB for frames of up to 2^25 pixels.
@@ -494,8 +497,19 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
         wrt::WavefrontArgs A;
         A.paths = ctx->d_wf_paths.p; A.queues = ctx->d_wf_queues.p; A.counters = ctx->d_wf_counters.p;
         A.accum = ctx->d_accum.p; A.capacity = n_slots; A.n_pixels = n_pixels;
+        A.sobol_matrices = nullptr;
+        if (sobol_sampler) {
+            if (!ctx->d_sobol_matrices.p) {
+                CU(ctx->d_sobol_matrices.ensure(1024 * 52));
+                CU(cudaMemcpyAsync(ctx->d_sobol_matrices.p, ctx->blob.matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            A.sobol_matrices = ctx->d_sobol_matrices.p;
+        }
         CU(cudaMemsetAsync(A.counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
         const uint32_t wf_grid = (uint32_t)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        int ext_blocks = 0;
+        CU(wrt::wf_extend_occupancy(&ext_blocks));
+        const uint32_t persist_grid = (uint32_t)ctx->sm_count * (uint32_t)std::max(ext_blocks, 1);
         CU(wrt::wf_launch_init(lp, A, wf_grid, ctx->stream));
         ++launches;
         // every slot runs chunk_size paths of at most max_depth segments, one segment per iteration
@@ -503,7 +517,7 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
         const uint32_t check_every = 16;
         bool done = false;
         for (uint64_t it = 0; it < max_iters && !done; ++it) {
-            CU(wrt::wf_launch_iteration(lp, A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, ctx->stream));
+            CU(wrt::wf_launch_iteration(lp, A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, persist_grid, ctx->stream));
             launches += 6;
             if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
                 CU(cudaMemcpyAsync(ctx->h_wf_counters, A.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -537,7 +551,7 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     // the lane-job kernel does not count paths: every (pixel, chunk) job runs all its samples
     const bool lane_job_kernel = !wavefront && packet && !sync_engine && !regroup_engine;
     ctx->stats.paths = wavefront ? wf_paths : (lane_job_kernel ? n_pixels64 * n_samples : counters[2]);
-    ctx->stats.traversal_steps = wavefront ? 0 : counters[3];
+    ctx->stats.traversal_steps = wavefront ? ctx->h_wf_counters[wrt::WF_STEPS] : counters[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;
     ctx->stats.kernel_ms_min = ctx->stats.kernel_ms_max = ms_kernel;

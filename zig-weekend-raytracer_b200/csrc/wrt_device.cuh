@@ -182,8 +182,13 @@ __device__ __forceinline__ d3 onb_transform(const Onb& b, d3 p) {  // math.zig:8
 // ---------------------------------------------------------------------------------------------------------
 // Draw layout: draws 0,1 = lens sample, 2 = ray time; bounce b owns draws 4+4b .. 4+4b+3 =
 // {mixture choice | Fresnel uniform, light pick, u1, u2}.  One Philox block yields the two draws of an even/odd pair.
+// With `sobol` set (WRT_FLAG_SAMPLER_SOBOL) the same draw slots are filled from the pixel sample's Sobol point instead:
+// draw j is sampleDimension(2 + j mod 1022) of the sample's global Sobol index — the reference's get1D / get2D counter that
+// starts at dimension 2 and wraps at 1024 (sampler.zig:203-220) — Owen-scrambled per dimension (sampler.zig:236-247).
 struct Rng {
     uint32_t k0, k1, pixel, sample;
+    const uint32_t* sobol = nullptr;  // SobolMatrices32, 1024 x 52 (global memory); nullptr = Philox
+    uint64_t sobol_index = 0;         // global Sobol index of (pixel, sample): sobolIntervalToIndex
 };
 
 __device__ __forceinline__ void philox_block(const Rng& r, uint32_t block, uint64_t& lo, uint64_t& hi) {
@@ -203,13 +208,7 @@ __device__ __forceinline__ void philox_block(const Rng& r, uint32_t block, uint6
     hi = (uint64_t)c2 | ((uint64_t)c3 << 32);
 }
 __device__ __forceinline__ double bits_to_unit(uint64_t bits) { return (double)(bits >> 11) * 0x1p-53; }  // 53 bits in [0,1)
-// draws (2*block, 2*block + 1) as uniforms
-__device__ __forceinline__ void rng_pair(const Rng& r, uint32_t block, double& a, double& b) {
-    uint64_t lo, hi;
-    philox_block(r, block, lo, hi);
-    a = bits_to_unit(lo);
-    b = bits_to_unit(hi);
-}
+__device__ __forceinline__ void rng_pair(const Rng& r, uint32_t block, double& a, double& b);  // draws (2*block, 2*block + 1)
 __device__ __forceinline__ uint32_t pick_index(double u, uint32_t n) {  // intRangeAtMost(0, n-1) stand-in
     uint32_t i = (uint32_t)(u * (double)n);
     return i < n ? i : n - 1;
@@ -295,6 +294,29 @@ __device__ __forceinline__ uint32_t murmur2_u32(uint32_t v, uint32_t seed) {  //
     h1 *= m;
     h1 ^= h1 >> 15;
     return h1;
+}
+
+// sampleDimension (sampler.zig:236-247) with the owen_fast randomiser: XOR of the dimension's matrix columns over the set
+// bits of the index, then the Laine-Karras hash seeded per dimension through Murmur2 (seed = low word of the render seed).
+__device__ __forceinline__ double sobol_dimension_unit(const Rng& r, uint32_t dimension) {
+    uint32_t v = 0;
+    uint64_t a = r.sobol_index;
+    for (uint32_t k = dimension * 52u; a != 0; a >>= 1, ++k)
+        if (a & 1) v ^= __ldg(r.sobol + k);
+    v = owen_fast_apply(murmur2_u32(dimension, r.k0), v);
+    return (double)sobol_sample_bits_to_float(v);
+}
+// draws (2*block, 2*block + 1) as uniforms in [0, 1)
+__device__ __forceinline__ void rng_pair(const Rng& r, uint32_t block, double& a, double& b) {
+    if (r.sobol) {  // folds away in the kernels that never set it (the megakernels)
+        a = sobol_dimension_unit(r, 2u + (2u * block) % 1022u);
+        b = sobol_dimension_unit(r, 2u + (2u * block + 1u) % 1022u);
+        return;
+    }
+    uint64_t lo, hi;
+    philox_block(r, block, lo, hi);
+    a = bits_to_unit(lo);
+    b = bits_to_unit(hi);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -423,6 +445,25 @@ __device__ __forceinline__ double div_zero_aware(double x, double y) {
     return x / y;
 }
 
+// Plane distance t = num / denom of QuadEntity.hit (entity.zig:482-486), formed only when it can lie in [tmin, tmax].
+// The reference always divides and then rejects t outside the interval; most quads a ray meets are behind it or beyond the
+// closest hit so far, and an IEEE binary64 division is ~20 instructions here (10 % of the packet kernel's instructions were
+// this division).  Rejections that need no quotient, both safe against the reference's rounded compare:
+//   tmin > 0 and (num == 0 or sign(num) != sign(denom))      =>  t <= 0 < tmin
+//   |num| > tmax * |denom| * (1 + 1e-12)                      =>  |t| > tmax by far more than the quotient's half ulp
+// Otherwise the quotient is formed (num != 0 when tmin > 0, so the zero-numerator slow path is never taken) and the
+// reference's own compare decides.  Returns false when the quad is rejected; t is valid only when it returns true.
+__device__ __forceinline__ bool quad_plane_t(double num, double denom, double tmin, double tmax, double& t) {
+    if (tmin > 0.0) {
+        if (num == 0.0 || ((__double2hiint(num) ^ __double2hiint(denom)) < 0)) return false;
+        if (fabs(num) > tmax * fabs(denom) * 1.000000000001) return false;
+        t = num / denom;
+    } else {
+        t = div_zero_aware(num, denom);
+    }
+    return (tmin <= t) && (t <= tmax);
+}
+
 // isInteriorPoint (entity.zig:527-541) decides on alpha = w . (planar x v) and beta = w . (u x planar), 28 binary64
 // operations after 6 loads.  Both are linear in `planar`, so alpha' = planar . (v x w) and beta' = planar . (w x u) — 10
 // operations, 3 loads — equal them up to rounding (a few 1e-16 times the size of the terms).  The traversals decide on
@@ -502,8 +543,8 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
             d3 n = mk(n0.x, n0.y, n1.x);
             double denom = dot(n, d);
             if (!(fabs(denom) < 1e-8)) {
-                double t = div_zero_aware(n1.y - dot(n, o), denom);
-                if ((tmin <= t) && (t <= best.t)) {
+                double t;
+                if (quad_plane_t(n1.y - dot(n, o), denom, tmin, best.t, t)) {
                     double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
                     double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
                     d3 p = o + d * t;
@@ -599,20 +640,9 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, ui
     }
 }
 
-// One pop or one op of the current leaf range.  Returns true when the traversal is complete.
-__device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
-                                               double tmin, double tmax) {
-    if (T.pc >= T.end) {  // range exhausted: pop
-        while (T.sp > 0) {
-            const uint4 e = stack[--T.sp];
-            if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
-            if (e.z != T.xf) { T.xf = e.z; ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
-            if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
-            else { T.node = WRT_NONE; T.pc = e.x; T.end = e.y; }
-            return false;
-        }
-        return true;
-    }
+// One op of the current leaf range (T.pc < T.end).
+__device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
+                                             double tmin, double tmax) {
     const uint32_t pc = T.pc;
     const uint4 op = __ldg(S.ops + pc);
     const d3 o = T.o, d = T.d;
@@ -651,8 +681,8 @@ __device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, ui
         d3 n = mk(n0.x, n0.y, n1.x);
         double denom = dot(n, d);
         if (!(fabs(denom) < 1e-8)) {
-            double t = div_zero_aware(n1.y - dot(n, o), denom);
-            if ((tmin <= t) && (t <= T.best_t)) {
+            double t;
+            if (quad_plane_t(n1.y - dot(n, o), denom, tmin, T.best_t, t)) {
                 double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);
                 d3 p = o + d * t;
                 d3 planar = p - mk(s0.x, s0.y, s1.x);
@@ -679,6 +709,28 @@ __device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, ui
     } else {
         T.pc = T.end;  // OP_END
     }
+}
+
+// Range exhausted: resume the nearest deferred subtree that can still hold a closer hit.  Returns true when the stack is
+// empty (the traversal is complete).
+__device__ __forceinline__ bool trav_pop(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd) {
+    while (T.sp > 0) {
+        const uint4 e = stack[--T.sp];
+        if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
+        if (e.z != T.xf) { T.xf = e.z; ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
+        if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
+        else { T.node = WRT_NONE; T.pc = e.x; T.end = e.y; }
+        return false;
+    }
+    return true;
+}
+
+// One op of the current leaf range (if any is left), then — when that exhausted the range — the pop, so a single-primitive
+// leaf costs one step and leaves the lane on its next record.  Returns true when the traversal is complete.
+__device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
+                                               double tmin, double tmax) {
+    if (T.pc < T.end) trav_leaf_op(S, T, stack, wo, wd, time, tmin, tmax);
+    if (T.node == WRT_NONE && T.pc >= T.end) return trav_pop(S, T, stack, wo, wd);
     return false;
 }
 
@@ -771,8 +823,8 @@ __device__ inline ClosestHit closest_hit_packet(const DeviceScene& S, bool activ
                 d3 n = mk(n0.x, n0.y, n1.x);
                 double denom = dot(n, d);
                 if (!(fabs(denom) < 1e-8)) {
-                    double t = div_zero_aware(n1.y - dot(n, o), denom);
-                    if ((tmin <= t) && (t <= best.t)) {
+                    double t;
+                    if (quad_plane_t(n1.y - dot(n, o), denom, tmin, best.t, t)) {
                         double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);
                         d3 p = o + d * t;
                         d3 planar = p - mk(s0.x, s0.y, s1.x);
@@ -916,8 +968,8 @@ __device__ inline double light_pdf_value_one(const SphereGeom* __restrict__ sphe
         d3 n = mk(n0.x, n0.y, n1.x);
         double denom = dot(n, direction);
         if (fabs(denom) < 1e-8) return 0.0;
-        double t = div_zero_aware(n1.y - dot(n, origin), denom);
-        if (!((1e-3 <= t) && (t <= CUDART_INF))) return 0.0;
+        double t;
+        if (!quad_plane_t(n1.y - dot(n, origin), denom, 1e-3, CUDART_INF, t)) return 0.0;
         const double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);  // start, area
         d3 p = origin + direction * t;
         d3 planar = p - mk(s0.x, s0.y, s1.x);
@@ -940,11 +992,16 @@ __device__ inline double light_pdf_value_one(const SphereGeom* __restrict__ sphe
         double disc = h * h - a * c;
         if (disc < 0.0) return 0.0;
         double sq = sqrt(disc);
-        double root = (h - sq) / a;
-        if (!((1e-3 < root) && (root < CUDART_INF))) {
-            root = (h + sq) / a;
-            if (!((1e-3 < root) && (root < CUDART_INF))) return 0.0;
-        }
+        // SphereEntity.pdfValue only asks WHETHER a root lies in (1e-3, inf) (entity.zig:630-633): decided on the numerator
+        // against 1e-3 * a (a > 0) unless the two are within 1e-12 of each other, where the reference's quotient is formed
+        auto root_in_range = [a](double numr) {
+            const double lim = 1e-3 * a;
+            if (numr > lim * 1.000000000001 && numr <= 1.7e308) return true;
+            if (numr < lim * 0.999999999999) return false;
+            const double root = numr / a;
+            return (1e-3 < root) && (root < CUDART_INF);
+        };
+        if (!root_in_range(h - sq) && !root_in_range(h + sq)) return 0.0;
         d3 diff = center - origin;
         double dist_sq = dot(diff, diff);
         double cos_theta_max = sqrt(1.0 - g.radius * g.radius / dist_sq);

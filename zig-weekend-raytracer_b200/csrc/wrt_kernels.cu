@@ -1035,6 +1035,8 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant_
             const uint32_t s = A.paths[slot].sample;
             rng.pixel = row * rc.width + col;
             rng.sample = s;
+            rng.sobol = A.sobol_matrices;
+            if (rng.sobol) rng.sobol_index = sobol_interval_to_index(LP.sobol, s, col, row);
             const Ray r = sample_ray(rc, LP.sobol, col, row, s, rc.dof != 0, S.has_moving != 0, &rng);
             PathState P;
             P.ox = r.o.x; P.oy = r.o.y; P.oz = r.o.z; P.dx = r.d.x; P.dy = r.d.y; P.dz = r.d.z;
@@ -1097,7 +1099,110 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
     }
 }
 
-template <int QUEUE>
+// Persistent form of wf_extend for the ordered per-lane traversal (large programs): every LANE owns one ray at a time and
+// takes the next ray of the extend queue the moment its traversal ends, so no lane waits for the longest traversal of its
+// warp (in render_kernel<.,lane> the node loop of the 2^20-primitive scene runs with 4.4 of 32 lanes: traversal lengths are
+// heavy-tailed and a warp is as slow as its slowest ray).  Fetching a ray is cheap here — 48 bytes from the path pool — which
+// is what a megakernel cannot offer (there a refill is a whole shading step).  One outer iteration: refill | child-pair records
+// for the lanes that stand on one, while they are at least half of the live lanes | leaf ops + pops for the others | retire.
+// The traversal functions are closest_hit_ordered's, the visiting order per ray is identical, so are the results.
+#ifndef WRT_WF_NODE_BURST
+#define WRT_WF_NODE_BURST 16
+#endif
+#ifndef WRT_WF_LEAF_BURST
+#define WRT_WF_LEAF_BURST 2
+#endif
+#ifndef WRT_WF_EXTEND_MIN_BLOCKS
+#define WRT_WF_EXTEND_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    const RenderConstants& rc = LP.rc;
+    const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
+    const uint32_t n = (uint32_t)A.counters[q_in];
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n);  // rays = closest-hit queries
+    const uint32_t* __restrict__ queue = wf_queue(A, q_in);
+    unsigned long long* cursor = &A.counters[WF_CURSOR];
+    Trav T;
+    uint4 stack[WRT_STACK_DEPTH];
+    d3 wo = mk(0, 0, 0), wd = mk(0, 0, 1);
+    double time = 0.0;
+    uint32_t slot = 0;
+    bool has = false, drained = false;
+    T.node = WRT_NONE; T.pc = 0; T.end = 0; T.sp = 0;
+    unsigned long long steps = 0;
+    for (;;) {
+        // ---- refill: lanes without a ray draw the next queue entries with one atomic per warp ----
+        const bool want = !has && !drained;
+        const unsigned wanting = __ballot_sync(0xffffffffu, want);
+        if (wanting) {
+            const int leader = __ffs(wanting) - 1;
+            unsigned long long first = 0;
+            if ((int)lane == leader) first = atomicAdd(cursor, (unsigned long long)__popc(wanting));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if (want) {
+                const unsigned long long mine = first + __popc(wanting & ((1u << lane) - 1u));
+                if (mine < n) {
+                    slot = __ldg(queue + mine);
+                    const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
+                    const double2 a = p[0], b = p[1], c = p[2];
+                    wo = mk(a.x, a.y, b.x); wd = mk(b.y, c.x, c.y);
+                    if (S.has_moving) time = A.paths[slot].time;
+                    trav_init(S, T, wo, wd, time, 1e-4, CUDART_INF);
+                    has = true;
+                } else {
+                    drained = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, has)) break;
+        // ---- node phase: binary32 child-pair records, while at least half of the lanes that hold a ray stand on one ----
+        const int n_has = __popc(__ballot_sync(0xffffffffu, has));
+#pragma unroll 1
+        for (int k = 0; k < WRT_WF_NODE_BURST; ++k) {
+            const bool in_node = has && T.node != WRT_NONE;
+            const int n_node = __popc(__ballot_sync(0xffffffffu, in_node));
+            if (n_node == 0 || (k > 0 && 2 * n_node < n_has)) break;
+            if (in_node) { trav_node_step(S, T, stack); ++steps; }
+        }
+        // ---- leaf phase: ops of leaf ranges (binary64 primitive tests, transforms, nested roots) and pops, for the others ----
+        bool done = false;
+#pragma unroll 1
+        for (int k = 0; k < WRT_WF_LEAF_BURST; ++k) {
+            const bool in_leaf = has && !done && T.node == WRT_NONE;
+            if (!__any_sync(0xffffffffu, in_leaf)) break;
+            if (in_leaf) { done = trav_leaf_step(S, T, stack, wo, wd, time, 1e-4, CUDART_INF); ++steps; }
+        }
+        // ---- retire finished rays (warp-uniform: the queue appends are ballots) ----
+        const bool fin = has && done;
+        if (__any_sync(0xffffffffu, fin)) {
+            int route = -1;
+            bool regen = false;
+            if (fin) {
+                const ClosestHit ch = trav_result(T);
+                if (ch.pc == WRT_NONE) {  // miss: L += beta * background, path ends (render.zig:215-217)
+                    PathState P = A.paths[slot];
+                    d3 L = mk(P.lx, P.ly, P.lz) + mk(P.bx, P.by, P.bz) * ld3(rc.background);
+                    regen = wf_finish_path(rc, A, slot, P, L);
+                } else {
+                    PathState* P = A.paths + slot;
+                    P->t = ch.t; P->hit_pc = ch.pc; P->hit_xf = ch.xform;
+                    const uint32_t kind = S.materials[__ldg(&S.ops[ch.pc].z)].kind;
+                    route = (kind == WRT_MAT_METAL) ? WQ_METAL : ((kind == WRT_MAT_LAMBERTIAN || kind == WRT_MAT_ISOTROPIC) ? WQ_SURFACE : WQ_OTHER);
+                }
+                has = false;
+            }
+            wf_push(A, WQ_SURFACE, route == WQ_SURFACE, slot);
+            wf_push(A, WQ_METAL, route == WQ_METAL, slot);
+            wf_push(A, WQ_OTHER, route == WQ_OTHER, slot);
+            wf_push(A, q_regen, regen, slot);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, off);
+    if (lane == 0 && steps) atomicAdd(&A.counters[WF_STEPS], steps);
+}
+
+template <int QUEUE, bool MANY_LIGHTS = false>
 __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     const RenderConstants& rc = LP.rc;
     const int q_extend = WQ_EXTEND0 + (int)(parity ^ 1u), q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
@@ -1116,6 +1221,8 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
             wf_slot_pixel(rc, A, slot, chunk, col, row);
             rng.pixel = row * rc.width + col;
             rng.sample = P.sample;
+            rng.sobol = A.sobol_matrices;
+            if (rng.sobol) rng.sobol_index = sobol_interval_to_index(LP.sobol, P.sample, col, row);
             Ray ray;
             ray.o = mk(P.ox, P.oy, P.oz); ray.d = mk(P.dx, P.dy, P.dz); ray.time = P.time;
             d3 beta = mk(P.bx, P.by, P.bz), L = mk(P.lx, P.ly, P.lz);
@@ -1130,7 +1237,7 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
                 if (M.kind == WRT_MAT_DIELECTRIC) cont = shade_dielectric(rec, M, ray, rng, bounce);
                 else cont = shade_emissive(S, rec, M, beta, L);
             } else {
-                cont = shade_surface(S, rec, M, ray, beta, L, rng, bounce);
+                cont = shade_surface<MANY_LIGHTS>(S, rec, M, ray, beta, L, rng, bounce);
             }
             const uint32_t depth_left = P.depth_left - 1;
             if (!cont || depth_left == 0) {
@@ -1160,6 +1267,7 @@ __global__ void wf_reset_kernel(const __grid_constant__ LaunchParams LP, Wavefro
         A.counters[WQ_SURFACE] = 0;
         A.counters[WQ_METAL] = 0;
         A.counters[WQ_OTHER] = 0;
+        A.counters[WF_CURSOR] = 0;
     }
 }
 
@@ -1257,14 +1365,27 @@ cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint3
     return cudaGetLastError();
 }
 // One wavefront iteration: generate -> extend -> shade (surface, metal, other) -> reset of the consumed queues.
+cudaError_t wf_extend_occupancy(int* blocks_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel, 128, 0);
+}
 cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
-                                uint32_t grid, cudaStream_t stream) {
+                                uint32_t grid, uint32_t persist_grid, cudaStream_t stream) {
     wf_generate_kernel<<<grid, 256, 0, stream>>>(lp, A, S, parity);
-    dispatch(cull_mode, packet, [&](auto c, auto t) {
-        wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
-    });
-    wf_shade_kernel<WQ_SURFACE><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
-    wf_shade_kernel<WQ_METAL><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    const bool ordered = !packet && cull_mode != WRT_CULL_REFERENCE && S.use_ordered;
+    if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)
+        wf_extend_ordered_kernel<<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+    } else {
+        dispatch(cull_mode, packet, [&](auto c, auto t) {
+            wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+        });
+    }
+    if (packet) {
+        wf_shade_kernel<WQ_SURFACE, false><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+        wf_shade_kernel<WQ_METAL, false><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    } else {  // large scenes: the light-list pdf skips lights whose box the ray misses (same sums)
+        wf_shade_kernel<WQ_SURFACE, true><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+        wf_shade_kernel<WQ_METAL, true><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
+    }
     wf_shade_kernel<WQ_OTHER><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);
     wf_reset_kernel<<<1, 32, 0, stream>>>(lp, A, parity);
     return cudaGetLastError();

@@ -50,7 +50,9 @@ struct __align__(16) PathState {  // 128 bytes, one L2 line per slot
 static_assert(sizeof(PathState) == 128, "PathState must stay one cache line");
 
 enum { WQ_EXTEND0 = 0, WQ_EXTEND1, WQ_REGEN0, WQ_REGEN1, WQ_SURFACE, WQ_METAL, WQ_OTHER, WQ_COUNT };
-// counters: [0..WQ_COUNT) queue sizes, [8] rays, [9] paths started, [10] slots finished
+// counters: [0..WQ_COUNT) queue sizes, [8] rays, [9] paths started, [10] slots finished, [11] read cursor of the persistent
+// extend kernel, [12] traversal steps
+enum { WF_CURSOR = 11, WF_STEPS = 12 };
 
 struct WavefrontArgs {
     PathState* paths;
@@ -59,12 +61,14 @@ struct WavefrontArgs {
     double* accum;                // [slot][3]
     uint32_t capacity;            // number of slots
     uint32_t n_pixels;            // pixels of this shard (slot % n_pixels = local pixel)
+    const uint32_t* sobol_matrices;  // WRT_FLAG_SAMPLER_SOBOL: SobolMatrices32 (1024 x 52), else nullptr
 };
 
 struct LaunchParams;
 cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint32_t grid, cudaStream_t stream);
 cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
-                                uint32_t grid, cudaStream_t stream);
+                                uint32_t grid, uint32_t persist_grid, cudaStream_t stream);
+cudaError_t wf_extend_occupancy(int* blocks_per_sm);
 
 cudaError_t launch_render(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream);
