@@ -44,7 +44,7 @@ def test_reference_tree_switch_keeps_the_reference_topology(wrt, wro):
     finally:
         del os.environ["WRT_REFERENCE_TREE"]
     assert (ref.n_ops, ref.n_prims) == (sah.n_ops, sah.n_prims)
-    assert ref.n_tree_records <= sah.n_tree_records           # the rebuilt trees append their records
+    assert ref.n_tree_records > 0 and sah.n_tree_records > 0   # four-wide records of either topology
     assert ref.tree_depth == 9                                 # balanced median split over 484 + 4 leaves (entity.zig:226-259)
     sc.close()
 

@@ -83,7 +83,7 @@ extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, cha
     info->n_ops_packet = (uint32_t)(cs.ops_pruned.empty() ? cs.ops.size() : cs.ops_pruned.size());
     info->n_prims = cs.n_prims;
     info->n_boxes = (uint32_t)cs.boxes_tight.size();
-    info->n_tree_records = (uint32_t)cs.nodes2.size();
+    info->n_tree_records = (uint32_t)(WRT_WIDE_TREE ? cs.nodes4.size() : cs.nodes2.size());
     info->max_nesting = cs.max_nesting;
     info->n_lights = (uint32_t)cs.lights.size();
     info->ref_boxes_loose = cs.ref_boxes_loose;
@@ -141,7 +141,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     wrt::comm_release(ctx);
     ctx->d_shard.release(); ctx->d_staging.release();
     ctx->free_images();
-    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_spheres.release();
+    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_nodes4.release(); ctx->d_root4.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
@@ -228,6 +228,8 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
     CU(ctx->d_boxes_tight.upload(cs.boxes_tight, ctx->stream));
     CU(ctx->d_nodes2.upload(cs.nodes2, ctx->stream));
+    CU(ctx->d_nodes4.upload(cs.nodes4, ctx->stream));
+    CU(ctx->d_root4.upload(cs.root4, ctx->stream));
     CU(ctx->d_spheres.upload(cs.spheres, ctx->stream));
     CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
     CU(ctx->d_quads.upload(cs.quads, ctx->stream));
@@ -239,7 +241,7 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     CU(ctx->d_light_boxes.upload(cs.light_boxes, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     wrt::DeviceScene& ds = ctx->ds;
-    ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p; ds.nodes2 = ctx->d_nodes2.p;
+    ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p; ds.nodes2 = ctx->d_nodes2.p; ds.nodes4 = ctx->d_nodes4.p; ds.root4 = ctx->d_root4.p;
     ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
     ds.xforms = ctx->d_xforms.p; ds.xform_chains = ctx->d_xform_chains.p; ds.materials = ctx->d_materials.p; ds.textures = ctx->d_textures.p;
     ds.images = ctx->d_images.p; ds.lights = ctx->d_lights.p; ds.light_boxes = ctx->d_light_boxes.p;

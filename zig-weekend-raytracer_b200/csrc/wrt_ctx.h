@@ -68,6 +68,8 @@ struct wrt_ctx {
     wrt::DevBuf<wrt::BoxRef> d_boxes_ref;
     wrt::DevBuf<wrt::BoxTight> d_boxes_tight;
     wrt::DevBuf<wrt::Node2> d_nodes2;
+    wrt::DevBuf<wrt::Node4> d_nodes4;
+    wrt::DevBuf<uint32_t> d_root4;
     wrt::DevBuf<wrt::SphereGeom> d_spheres;
     wrt::DevBuf<wrt::SphereAux> d_sphere_aux;
     wrt::DevBuf<wrt::QuadGeom> d_quads;

@@ -49,6 +49,14 @@ struct __align__(16) Node2 {
     float rmin[3]; uint32_t r_desc;
     float rmax[3]; uint32_t r_end;
 };
+// Four-wide record of the ordered traversal (one 128-byte line): the binary SAH tree collapsed two levels at a time
+// (wrt_program.cu: build_nodes4), children's binary32 boxes as structure of arrays.  desc: bit 31 set = inner record index,
+// otherwise first op of a leaf range ending at `end`; WRT_NONE = empty slot.
+struct __align__(16) Node4 {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    uint32_t desc[4];
+    uint32_t end[4];
+};
 struct __align__(16) SphereGeom { // entity.zig:536-537
     double cx, cy, cz, radius;
 };
@@ -93,6 +101,8 @@ struct DeviceScene {
     const BoxRef* boxes_ref;
     const BoxTight* boxes_tight;
     const Node2* nodes2;
+    const Node4* nodes4;           // four-wide records (ordered traversal)
+    const uint32_t* root4;         // per box index: the Node4 record of the tree rooted there (WRT_NONE if it is not a root)
     const SphereGeom* spheres;
     const SphereAux* sphere_aux;
     const QuadGeom* quads;
@@ -583,6 +593,9 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 // unless a later one is a quad, in which case the last such quad wins.  Ops are numbered in DFS order, so tracking
 // (first op, last quad op) of the minimal-t set reproduces that rule under any visiting order.
 #define WRT_STACK_DEPTH 48
+#ifndef WRT_WIDE_TREE
+#define WRT_WIDE_TREE 1  // ordered traversal over the four-wide records (Node4); 0 = the child-pair records (Node2)
+#endif
 // The traversal state.
 struct Trav {
     double best_t;
@@ -640,6 +653,47 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, ui
     }
 }
 
+// One four-wide record: test the (up to) four children, go to the nearest one that is hit, defer the others so that the
+// nearer ones are popped first.  Order only steers the search (closest hit and tie rule do not depend on it), so the sort
+// runs on truncated keys: entry distance bits with the child index in the low two mantissa bits.
+__device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+    const float4* p = reinterpret_cast<const float4*>(S.nodes4 + T.node);
+    const float4 lox = __ldg(p), loy = __ldg(p + 1), loz = __ldg(p + 2), hix = __ldg(p + 3), hiy = __ldg(p + 4), hiz = __ldg(p + 5);
+    const uint4 desc = __ldg(reinterpret_cast<const uint4*>(p) + 6), end = __ldg(reinterpret_cast<const uint4*>(p) + 7);
+    const float t_hi = __double2float_ru(T.best_t);
+    float e0, e1, e2, e3;
+    const bool h0 = T.cull.entry(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, T.t_lo, t_hi, e0) && desc.x != WRT_NONE;
+    const bool h1 = T.cull.entry(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, T.t_lo, t_hi, e1) && desc.y != WRT_NONE;
+    const bool h2 = T.cull.entry(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, T.t_lo, t_hi, e2) && desc.z != WRT_NONE;
+    const bool h3 = T.cull.entry(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, T.t_lo, t_hi, e3) && desc.w != WRT_NONE;
+    const uint32_t miss = 0x7F800000u;  // +inf: sorts last
+    uint32_t k0 = h0 ? ((__float_as_uint(fmaxf(e0, 0.0f)) & ~3u) | 0u) : (miss | 0u);
+    uint32_t k1 = h1 ? ((__float_as_uint(fmaxf(e1, 0.0f)) & ~3u) | 1u) : (miss | 1u);
+    uint32_t k2 = h2 ? ((__float_as_uint(fmaxf(e2, 0.0f)) & ~3u) | 2u) : (miss | 2u);
+    uint32_t k3 = h3 ? ((__float_as_uint(fmaxf(e3, 0.0f)) & ~3u) | 3u) : (miss | 3u);
+#define WRT_CSWAP(a, b) { const uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+    WRT_CSWAP(k0, k1) WRT_CSWAP(k2, k3) WRT_CSWAP(k0, k2) WRT_CSWAP(k1, k3) WRT_CSWAP(k1, k2)
+#undef WRT_CSWAP
+    auto pick_u = [](const uint4& v, uint32_t i) { return (i & 2u) ? ((i & 1u) ? v.w : v.z) : ((i & 1u) ? v.y : v.x); };
+    auto pick_e = [&](uint32_t i) { return (i & 2u) ? ((i & 1u) ? e3 : e2) : ((i & 1u) ? e1 : e0); };
+    // defer the far ones, farthest first (k3 >= k2 >= k1): the entry distance kept for the pop-time cull is the exact one
+    if (k3 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k3 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
+    if (k2 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k2 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
+    if (k1 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k1 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
+    if (k0 < miss) {
+        const uint32_t i = k0 & 3u, go = pick_u(desc, i);
+        if (go & 0x80000000u) { T.node = go & 0x7FFFFFFFu; }
+        else { T.node = WRT_NONE; T.pc = go; T.end = pick_u(end, i); }
+        return;
+    }
+    T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
+}
+
+__device__ __forceinline__ void trav_record_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+    if (WRT_WIDE_TREE) trav_node4_step(S, T, stack);
+    else trav_node_step(S, T, stack);
+}
+
 // One op of the current leaf range (T.pc < T.end).
 __device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
                                              double tmin, double tmax) {
@@ -648,7 +702,7 @@ __device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint
     const d3 o = T.o, d = T.d;
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
         if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
-        T.node = op.y;
+        T.node = WRT_WIDE_TREE ? __ldg(S.root4 + op.y) : op.y;
     } else if (op.x == OP_NODE_TIGHT_ONLY) {
         T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
     } else if (op.x == OP_SPHERE) {
@@ -750,7 +804,7 @@ __device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3
     // "while-while": every lane first descends through box records until it stands on a leaf range (cheap binary32 steps),
     // then the lanes of the warp run their binary64 primitive tests together
     for (;;) {
-        while (T.node != WRT_NONE) trav_node_step(S, T, stack);
+        while (T.node != WRT_NONE) trav_record_step(S, T, stack);
         if (trav_leaf_step(S, T, stack, wo, wd, time, tmin, tmax)) break;
     }
     return trav_result(T);

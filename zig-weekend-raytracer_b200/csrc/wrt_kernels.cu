@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
             const bool in_node = has && T.node != WRT_NONE;
             const int n_node = __popc(__ballot_sync(0xffffffffu, in_node));
             if (n_node == 0 || (k > 0 && 2 * n_node < n_has)) break;
-            if (in_node) { trav_node_step(S, T, stack); ++steps; }
+            if (in_node) { trav_record_step(S, T, stack); ++steps; }
         }
         // ---- leaf phase: ops of leaf ranges (binary64 primitive tests, transforms, nested roots) and pops, for the others ----
         bool done = false;

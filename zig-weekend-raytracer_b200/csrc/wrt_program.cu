@@ -553,6 +553,79 @@ struct Compiler {
         }
     }
 
+    // Four-wide records: every tree of nodes2 (SAH-rebuilt or reference topology) collapsed top-down — a record starts with
+    // the two children of a child-pair record and, while it has a free slot, replaces the inner child with the largest box by
+    // that child's own two children.  Boxes, leaf ranges and therefore the set of primitives reached are those of nodes2;
+    // only the fan-out changes: half the dependent record fetches per ray, one 128-byte line each.
+    struct Child4 { float lo[3], hi[3]; uint32_t desc, end; };
+    static float area4(const Child4& c) {
+        const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? 0.0f : dx * dy + dy * dz + dz * dx;
+    }
+    static void children_of(const Node2& n, std::vector<Child4>& out4) {
+        Child4 c;
+        for (int k = 0; k < 3; ++k) { c.lo[k] = n.lmin[k]; c.hi[k] = n.lmax[k]; }
+        c.desc = n.l_desc; c.end = n.l_end;
+        if (c.desc != WRT_NONE) out4.push_back(c);
+        for (int k = 0; k < 3; ++k) { c.lo[k] = n.rmin[k]; c.hi[k] = n.rmax[k]; }
+        c.desc = n.r_desc; c.end = n.r_end;
+        if (c.desc != WRT_NONE) out4.push_back(c);
+    }
+    void build_nodes4() {
+        out.nodes4.clear();
+        out.root4.assign(out.nodes2.size(), WRT_NONE);
+        struct Work { uint32_t rec2, rec4; };
+        std::vector<Work> work;
+        for (const BvhRoot& r : bvh_roots) {
+            out.root4[r.record] = (uint32_t)out.nodes4.size();
+            out.nodes4.emplace_back();
+            work.push_back({r.record, out.root4[r.record]});
+            while (!work.empty()) {
+                const Work w = work.back();
+                work.pop_back();
+                std::vector<Child4> ch;
+                children_of(out.nodes2[w.rec2], ch);
+                for (;;) {  // widen: open the inner child with the largest box while a slot is free
+                    if (ch.size() >= 4) break;
+                    int best = -1;
+                    float best_area = -1.0f;
+                    for (size_t i = 0; i < ch.size(); ++i)
+                        if ((ch[i].desc & 0x80000000u) && area4(ch[i]) > best_area) { best = (int)i; best_area = area4(ch[i]); }
+                    if (best < 0) break;
+                    std::vector<Child4> sub;
+                    children_of(out.nodes2[ch[(size_t)best].desc & 0x7FFFFFFFu], sub);
+                    if (ch.size() - 1 + sub.size() > 4) break;
+                    ch.erase(ch.begin() + best);
+                    ch.insert(ch.end(), sub.begin(), sub.end());
+                }
+                Node4 n;
+                for (int i = 0; i < 4; ++i) {  // empty slot: a box nothing can hit, no child
+                    n.lox[i] = n.loy[i] = n.loz[i] = 1.0f; n.hix[i] = n.hiy[i] = n.hiz[i] = -1.0f;
+                    n.desc[i] = WRT_NONE; n.end[i] = 0;
+                }
+                for (size_t i = 0; i < ch.size(); ++i) {
+                    n.lox[i] = ch[i].lo[0]; n.loy[i] = ch[i].lo[1]; n.loz[i] = ch[i].lo[2];
+                    n.hix[i] = ch[i].hi[0]; n.hiy[i] = ch[i].hi[1]; n.hiz[i] = ch[i].hi[2];
+                    if (ch[i].desc & 0x80000000u) {
+                        const uint32_t rec4 = (uint32_t)out.nodes4.size();
+                        out.nodes4.emplace_back();
+                        work.push_back({ch[i].desc & 0x7FFFFFFFu, rec4});
+                        n.desc[i] = 0x80000000u | rec4; n.end[i] = 0;
+                    } else {
+                        n.desc[i] = ch[i].desc; n.end[i] = ch[i].end;
+                    }
+                }
+                out.nodes4[w.rec4] = n;
+            }
+        }
+        if (out.nodes4.empty()) {  // keep the device pointer non-null
+            Node4 n;
+            std::memset(&n, 0, sizeof n);
+            for (int i = 0; i < 4; ++i) n.desc[i] = WRT_NONE;
+            out.nodes4.push_back(n);
+        }
+    }
+
     // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` with the work removed that cannot pay for
     // itself when 32 rays share one program counter.  Tight boxes are conservative, so dropping a box test never changes a
     // result; WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
@@ -650,6 +723,7 @@ struct Compiler {
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
         rebuild_trees();
+        build_nodes4();
         prune_program();
         // transform chains in application order (outermost first), so the device needs no per-thread array
         out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
@@ -728,12 +802,13 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
             }
         }
     }
-    // ordered-traversal trees: from every bvh root (an OP_NODE not enclosed by another OP_NODE's own tree) the records must
-    // reach each primitive op of [pc + 1, skip) exactly once (nested trees are entered through their own root op)
+    // ordered-traversal trees: from every bvh root (an OP_NODE met inside a leaf range, plus op 0) the records must reach each
+    // primitive op of [pc + 1, skip) exactly once (nested trees are entered through their own root op) — checked for the
+    // child-pair records (nodes2) and for the four-wide records the traversal walks (nodes4)
     std::vector<uint8_t> seen(n, 0);
-    std::vector<uint8_t> is_root(n, 0);
-    {   // a root = an OP_NODE that is not a direct descendant bvh_node of an open OP_NODE without a frame / collection boundary;
-        // the traversal itself tells: roots are the OP_NODE ops it meets INSIDE leaf ranges, plus op 0
+    for (int wide = 0; wide < 2; ++wide) {
+        std::fill(seen.begin(), seen.end(), 0);
+        const size_t n_records = wide ? cs.nodes4.size() : cs.nodes2.size();
         std::vector<std::pair<uint32_t, uint32_t>> ranges;  // leaf op ranges still to scan for nested roots
         ranges.push_back({0u, (uint32_t)n - 1});
         while (!ranges.empty()) {
@@ -748,22 +823,32 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
                     ++pc;
                     continue;
                 }
-                is_root[pc] = 1;
                 // walk this tree's records
                 struct Item { uint32_t rec, depth; };
                 std::vector<Item> st;
-                st.push_back({op.y, 1u});
+                uint32_t root = op.y;
+                if (wide) {
+                    if (op.y >= cs.root4.size() || cs.root4[op.y] == WRT_NONE) { err = "bvh root without a four-wide record at op " + std::to_string(pc); return false; }
+                    root = cs.root4[op.y];
+                }
+                st.push_back({root, 1u});
                 size_t visited = 0;
                 while (!st.empty()) {
                     const Item it = st.back();
                     st.pop_back();
-                    if (it.rec >= cs.nodes2.size()) { err = "tree record index out of range"; return false; }
-                    if (++visited > cs.nodes2.size()) { err = "tree records form a cycle"; return false; }
-                    tree_depth = std::max(tree_depth, it.depth);
-                    const Node2& r = cs.nodes2[it.rec];
-                    const uint32_t desc[2] = {r.l_desc, r.r_desc}, end[2] = {r.l_end, r.r_end};
-                    for (int k = 0; k < 2; ++k) {
-                        if (desc[k] == WRT_NONE) { if (k == 0) { err = "tree record without a left child"; return false; } continue; }
+                    if (it.rec >= n_records) { err = "tree record index out of range"; return false; }
+                    if (++visited > n_records) { err = "tree records form a cycle"; return false; }
+                    if (!wide) tree_depth = std::max(tree_depth, it.depth);
+                    uint32_t desc[4] = {WRT_NONE, WRT_NONE, WRT_NONE, WRT_NONE}, end[4] = {0, 0, 0, 0};
+                    if (wide) {
+                        for (int k = 0; k < 4; ++k) { desc[k] = cs.nodes4[it.rec].desc[k]; end[k] = cs.nodes4[it.rec].end[k]; }
+                    } else {
+                        const Node2& r = cs.nodes2[it.rec];
+                        desc[0] = r.l_desc; desc[1] = r.r_desc; end[0] = r.l_end; end[1] = r.r_end;
+                        if (r.l_desc == WRT_NONE) { err = "tree record without a left child"; return false; }
+                    }
+                    for (int k = 0; k < 4; ++k) {
+                        if (desc[k] == WRT_NONE) continue;
                         if (desc[k] & 0x80000000u) st.push_back({desc[k] & 0x7FFFFFFFu, it.depth + 1});
                         else {
                             if (!(desc[k] > pc && end[k] > desc[k] && end[k] <= op.z)) { err = "tree leaf range outside its bvh at op " + std::to_string(pc); return false; }
@@ -774,17 +859,30 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
                 pc = op.z;  // the tree covered [pc + 1, skip)
             }
         }
+        for (size_t pc = 0; pc < n; ++pc)
+            if ((cs.ops[pc].x == OP_SPHERE || cs.ops[pc].x == OP_QUAD) && seen[pc] != 1) {
+                err = std::string("primitive op ") + std::to_string(pc) + " is not reachable through the " + (wide ? "four-wide" : "child-pair") + " records";
+                return false;
+            }
     }
-    for (size_t pc = 0; pc < n; ++pc)
-        if ((cs.ops[pc].x == OP_SPHERE || cs.ops[pc].x == OP_QUAD) && seen[pc] != 1) {
-            err = "primitive op " + std::to_string(pc) + " is not reachable through the ordered-traversal trees"; return false;
-        }
     return true;
 }
 
 namespace {
 uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi);
 uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard) {
+#if WRT_WIDE_TREE
+    if (rec >= cs.nodes4.size() || guard > 4096) return 1u << 20;  // malformed: never fits
+    const Node4& r = cs.nodes4[rec];
+    uint32_t need = 0, n_children = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (r.desc[k] == WRT_NONE) continue;
+        ++n_children;
+        const uint32_t c = (r.desc[k] & 0x80000000u) ? stack_need_record(cs, r.desc[k] & 0x7FFFFFFFu, guard + 1) : stack_need_range(cs, r.desc[k], r.end[k]);
+        need = std::max(need, c);
+    }
+    return need + (n_children ? n_children - 1 : 0u);  // the other children wait on the stack while one is descended
+#else
     if (rec >= cs.nodes2.size() || guard > 4096) return 1u << 20;  // malformed: never fits
     const Node2& r = cs.nodes2[rec];
     uint32_t need = 0;
@@ -796,13 +894,15 @@ uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard
     }
     const bool two = r.l_desc != WRT_NONE && r.r_desc != WRT_NONE;
     return need + (two ? 1u : 0u);  // the other child waits on the stack while this one is descended
+#endif
 }
 uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi) {
     uint32_t need = 0;
     for (uint32_t pc = lo; pc < hi && pc < cs.ops.size();) {
         const uint4 op = cs.ops[pc];
         if (op.x == OP_NODE) {  // nested tree: the rest of the range waits while it is descended
-            need = std::max(need, 1u + stack_need_record(cs, op.y, 0));
+            const uint32_t root = WRT_WIDE_TREE ? (op.y < cs.root4.size() ? cs.root4[op.y] : WRT_NONE) : op.y;
+            need = std::max(need, 1u + stack_need_record(cs, root, 0));
             pc = op.z > pc ? op.z : pc + 1;
         } else {
             ++pc;
