@@ -62,6 +62,10 @@ def parse_args():
     ap.add_argument("--impl", default="wrt", choices=["wrt", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cull", default="auto", choices=["auto", "tight", "reference"])
+    ap.add_argument("--warmup-spp", type=int, default=0, help="spp of the warm-up steps (0 = the workload's; for minute-long frames)")
+    ap.add_argument("--fused-e2e", action="store_true",
+                    help="minute-long frames: time each step ONCE — the e2e call (upload + render into host memory) — and take "
+                         "`value` from the device events of that same render instead of rendering every frame twice")
     ap.add_argument("--engine", default="auto", choices=["auto", "megakernel", "wavefront"], help="development: force an engine")
     ap.add_argument("--shard", default="rows", choices=["rows", "samples"], help="N > 1: what the devices split")
     ap.add_argument("--no-all-workloads", dest="all_workloads", action="store_false",
@@ -358,8 +362,13 @@ def main():
     fp64_peak = ctx.fp64_issue_peak() if rank == 0 else 0.0
     fp32_peak = ctx.fp32_issue_peak() if rank == 0 else 0.0
 
+    if args.warmup_spp:
+        full_spp = params.samples_per_pixel
+        params.samples_per_pixel = args.warmup_spp
     for _ in range(args.warmup):
         device_step()
+    if args.warmup_spp:
+        params.samples_per_pixel = full_spp
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -369,8 +378,19 @@ def main():
     rays = paths = 0
     dev_ms = kern_ms = gath_ms = 0.0
     launches = 0
+    e2e_rays = 0
     for _ in range(args.steps):
-        r, p_, ms, kms, gms, nl = device_step()
+        if args.fused_e2e:  # one render per step: the user-facing call, device-timed inside
+            ctx.upload_scene(flat)
+            if dist:
+                ctx.render_sharded(cam, params, out=h_fb.numpy() if rank == 0 else None)
+            else:
+                ctx.render(cam, params, lanes=LANES, out=h_fb.numpy())
+            st = ctx.stats()
+            r, p_, ms, kms, gms, nl = st.rays, st.paths, st.kernel_ms, st.kernel_ms, st.gather_ms, st.kernel_launches
+            e2e_rays += r
+        else:
+            r, p_, ms, kms, gms, nl = device_step()
         rays += r; paths += p_; dev_ms += ms + gms; kern_ms += kms; gath_ms += gms; launches += nl
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
@@ -394,8 +414,7 @@ def main():
     # ---- e2e: host buffers in, host framebuffer out, every step ----
     barrier()
     t0 = time.perf_counter()
-    e2e_rays = 0
-    for _ in range(args.steps):
+    for _ in range(0 if args.fused_e2e else args.steps):
         ctx.upload_scene(flat)  # H2D of the scene arrays (the step's inputs)
         if dist:
             ctx.render_sharded(cam, params, out=h_fb.numpy() if rank == 0 else None)  # gather + D2H of the full frame on rank 0
@@ -403,7 +422,7 @@ def main():
             ctx.render(cam, params, lanes=LANES, out=h_fb.numpy())  # D2H into the pinned host framebuffer
         e2e_rays += ctx.stats().rays
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = (wall_ms * 1e-3) if args.fused_e2e else (time.perf_counter() - t0)
     e = torch.tensor([e2e_rays], dtype=torch.float64, device=f"cuda:{local}")
     ts = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
     if dist:
@@ -435,7 +454,10 @@ def main():
                    "parallelism": (f"{'sample-range' if args.shard == 'samples' else 'row-interleaved'} shards x{n_gpus}"
                                    + (" + NCCL gather inside wrt_render_sharded" if n_gpus > 1 else "")),
                    "l2_policy": "scene is cache-resident by design; per-step traffic is the framebuffer (> L2 only for C5)",
-                   "textures": img_note, "reduced_spp": bool(args.spp), "reduced_frame": bool(args.res)},
+                   "textures": img_note, "reduced_spp": bool(args.spp), "reduced_frame": bool(args.res),
+                   "warmup_spp": args.warmup_spp or spp,
+                   "timing": ("fused: each step is ONE e2e call (upload + render into host memory); `value` = rays / device-event "
+                              "time of the kernel + gather of those same calls") if args.fused_e2e else "separate device-resident and e2e steps"},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "rays_per_step": rays_all / args.steps, "paths_per_step": paths_all / args.steps,
         "gather_ms_per_step": gath_ms_max / args.steps,

@@ -83,7 +83,7 @@ extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, cha
     info->n_ops_packet = (uint32_t)(cs.ops_pruned.empty() ? cs.ops.size() : cs.ops_pruned.size());
     info->n_prims = cs.n_prims;
     info->n_boxes = (uint32_t)cs.boxes_tight.size();
-    info->n_tree_records = (uint32_t)(WRT_WIDE_TREE ? cs.nodes4.size() : cs.nodes2.size());
+    info->n_tree_records = (uint32_t)(cs.use_wide ? cs.nodes4.size() : cs.nodes2.size());
     info->max_nesting = cs.max_nesting;
     info->n_lights = (uint32_t)cs.lights.size();
     info->ref_boxes_loose = cs.ref_boxes_loose;
@@ -251,6 +251,7 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     ds.has_moving = cs.has_moving ? 1u : 0u;
     // ordered traversal only when its exact worst-case stack use fits (ordered_stack_depth walks the rebuilt trees)
     ds.use_ordered = (cs.stack_depth <= WRT_STACK_DEPTH) ? 1u : 0u;
+    ds.use_wide = cs.use_wide ? 1u : 0u;
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
     ctx->n_ops = cs.ops.size();
@@ -434,7 +435,12 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     const uint64_t base_jobs = (uint64_t)rc.n_rows_local * rc.n_col_blocks;
     // Engine: the persistent megakernel is the default — on the measured configs it matches the
     // wavefront (queues in HBM, one small kernel per stage) without its state traffic; the wavefront is selected by flag.
-    bool wavefront = false;
+    // Large trees (the four-wide records, i.e. scenes whose records do not stay in L1) default to the wavefront: its persistent
+    // extend kernel replaces every finished ray at once, which the heavy-tailed traversal lengths of such scenes need (the
+    // megakernel's node loop runs with 5 of 32 lanes there).  Everything else defaults to the megakernel.
+    bool wavefront = !packet && ctx->ds.use_wide && ctx->ds.use_ordered && p.cull_mode == WRT_CULL_TIGHT &&
+                     p.max_ray_bounce_depth > 0 && n_pixels64 > 0 && n_samples > 0 &&
+                     !(p.flags & (WRT_FLAG_ENGINE_SYNC | WRT_FLAG_ENGINE_REGROUP));
     if (p.flags & WRT_FLAG_ENGINE_MEGAKERNEL) wavefront = false;
     // the Sobol-dimension sampler lives in the wavefront kernels only (the megakernels sit at their register caps)
     const bool sobol_sampler = (p.flags & WRT_FLAG_SAMPLER_SOBOL) != 0;
@@ -449,7 +455,9 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     if (n_samples > 0) {
         uint64_t want, min_chunk;
         if (wavefront) {
-            want = ((4ull << 20) + frame_pixels - 1) / frame_pixels;  // pool of ~4M path slots: slot = (sample chunk, pixel)
+            // pool of ~16M path slots (slot = (sample chunk, pixel), 128 B of state each): a few million rays per launch and
+            // device even when eight GPUs share the frame, so the longest single traversal of a launch stays a small part of it
+            want = ((16ull << 20) + frame_pixels - 1) / frame_pixels;
             min_chunk = 1;
         } else {
             // 2^25 (pixel, chunk) jobs per frame: a few dozen per resident lane even when 8 GPUs share the frame.  The packet

@@ -114,7 +114,9 @@ struct DeviceScene {
     const Light* lights;
     const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
-    uint32_t use_ordered, _pad0, _pad1, _pad2;  // ordered traversal allowed (tree depth fits WRT_STACK_DEPTH)
+    uint32_t use_ordered;  // ordered traversal allowed (its worst-case stack use fits WRT_STACK_DEPTH)
+    uint32_t use_wide;     // the ordered traversal walks the four-wide records (large trees) instead of the child-pair records
+    uint32_t _pad1, _pad2;
 };
 
 struct SobolLut {                  // byte-indexed folds of the matrices below (global memory, L1 resident, 23 KB)
@@ -593,8 +595,11 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 // unless a later one is a quad, in which case the last such quad wins.  Ops are numbered in DFS order, so tracking
 // (first op, last quad op) of the minimal-t set reproduces that rule under any visiting order.
 #define WRT_STACK_DEPTH 48
-#ifndef WRT_WIDE_TREE
-#define WRT_WIDE_TREE 1  // ordered traversal over the four-wide records (Node4); 0 = the child-pair records (Node2)
+// Trees with at least this many child-pair records are walked through their four-wide form.  Measured: the 2^20-primitive
+// scene (latency-bound: its records miss L1) gains 22 % from half the dependent fetches, the 484-sphere scene (cache-resident,
+// issue-bound) loses 7 % to the extra box tests of records opened two levels at a time.
+#ifndef WRT_WIDE_TREE_MIN_RECORDS
+#define WRT_WIDE_TREE_MIN_RECORDS 16384u
 #endif
 // The traversal state.
 struct Trav {
@@ -690,19 +695,19 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, u
 }
 
 __device__ __forceinline__ void trav_record_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
-    if (WRT_WIDE_TREE) trav_node4_step(S, T, stack);
+    if (S.use_wide) trav_node4_step(S, T, stack);
     else trav_node_step(S, T, stack);
 }
 
 // One op of the current leaf range (T.pc < T.end).
-__device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
-                                             double tmin, double tmax) {
+template <typename WORLD>
+__device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
     const uint32_t pc = T.pc;
     const uint4 op = __ldg(S.ops + pc);
     const d3 o = T.o, d = T.d;
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
         if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
-        T.node = WRT_WIDE_TREE ? __ldg(S.root4 + op.y) : op.y;
+        T.node = S.use_wide ? __ldg(S.root4 + op.y) : op.y;
     } else if (op.x == OP_NODE_TIGHT_ONLY) {
         T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
     } else if (op.x == OP_SPHERE) {
@@ -712,7 +717,7 @@ __device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint
         const double radius = g1.y;
         if (S.has_moving) {
             const SphereAux ax = S.sphere_aux[op.y];
-            if (ax.is_moving) center = center + mk(ax.mx, ax.my, ax.mz) * time;
+            if (ax.is_moving) { d3 wo_, wd_; double time; world(wo_, wd_, time); center = center + mk(ax.mx, ax.my, ax.mz) * time; }
         }
         d3 oc = center - o;
         double a = dot(d, d);
@@ -757,7 +762,7 @@ __device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint
         T.pc = pc + 1;
     } else if (op.x == OP_POP) {
         T.xf = op.y;
-        ray_in_xform(S, T.xf, wo, wd, T.o, T.d);
+        { d3 wo, wd; double time; world(wo, wd, time); ray_in_xform(S, T.xf, wo, wd, T.o, T.d); }
         T.cull.set_ray(T.o, T.d);
         T.pc = pc + 1;
     } else {
@@ -767,11 +772,12 @@ __device__ __forceinline__ void trav_leaf_op(const DeviceScene& S, Trav& T, uint
 
 // Range exhausted: resume the nearest deferred subtree that can still hold a closer hit.  Returns true when the stack is
 // empty (the traversal is complete).
-__device__ __forceinline__ bool trav_pop(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd) {
+template <typename WORLD>
+__device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world) {
     while (T.sp > 0) {
         const uint4 e = stack[--T.sp];
         if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
-        if (e.z != T.xf) { T.xf = e.z; ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
+        if (e.z != T.xf) { T.xf = e.z; d3 wo, wd; double time; world(wo, wd, time); ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
         if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
         else { T.node = WRT_NONE; T.pc = e.x; T.end = e.y; }
         return false;
@@ -781,11 +787,16 @@ __device__ __forceinline__ bool trav_pop(const DeviceScene& S, Trav& T, uint4* _
 
 // One op of the current leaf range (if any is left), then — when that exhausted the range — the pop, so a single-primitive
 // leaf costs one step and leaves the lane on its next record.  Returns true when the traversal is complete.
+template <typename WORLD>
+__device__ __forceinline__ bool trav_leaf_step_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
+    if (T.pc < T.end) trav_leaf_op_lazy(S, T, stack, world, tmin, tmax);
+    if (T.node == WRT_NONE && T.pc >= T.end) return trav_pop_lazy(S, T, stack, world);
+    return false;
+}
+// the same with the world-space ray at hand (megakernels, gates)
 __device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
                                                double tmin, double tmax) {
-    if (T.pc < T.end) trav_leaf_op(S, T, stack, wo, wd, time, tmin, tmax);
-    if (T.node == WRT_NONE && T.pc >= T.end) return trav_pop(S, T, stack, wo, wd);
-    return false;
+    return trav_leaf_step_lazy(S, T, stack, [&](d3& o_, d3& d_, double& t_) { o_ = wo; d_ = wd; t_ = time; }, tmin, tmax);
 }
 
 __device__ __forceinline__ ClosestHit trav_result(const Trav& T) {

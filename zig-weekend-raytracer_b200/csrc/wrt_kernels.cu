@@ -1113,50 +1113,109 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
 #define WRT_WF_LEAF_BURST 2
 #endif
 #ifndef WRT_WF_EXTEND_MIN_BLOCKS
-#define WRT_WF_EXTEND_MIN_BLOCKS 4
+#define WRT_WF_EXTEND_MIN_BLOCKS 6  // <= 85 registers: 24 warps per SM (the kernel is bound by memory latency, not by issue)
 #endif
+#ifndef WRT_WF_CURSOR_CHUNK
+#define WRT_WF_CURSOR_CHUNK 256u    // most queue entries a warp draws per atomic
+#endif
+// Output queues are fed through per-warp staging rows in shared memory: a retiring lane drops its slot there and the warp
+// appends a full row of 32 with ONE atomic (the plain wf_push costs one atomic per warp per retire event, and with lanes
+// retiring one or two at a time four counters were taking 10^8 atomics a second).
+#define WRT_WF_STAGE 64  // entries per (warp, queue) row: < 32 before a retire event adds <= 32
+struct WfStage {
+    uint32_t slot[4][WRT_WF_STAGE];
+};
+__device__ __forceinline__ void wf_stage_push(const WavefrontArgs& A, WfStage& st, uint32_t& count, int row, int queue, bool pred, uint32_t slot, uint32_t lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    if (pred) st.slot[row][count + __popc(mask & ((1u << lane) - 1u))] = slot;
+    count += __popc(mask);
+    __syncwarp();
+    if (count >= 32u) {  // append the oldest 32, keep the rest
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&A.counters[queue], 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        wf_queue(A, queue)[base + lane] = st.slot[row][lane];
+        __syncwarp();
+        const uint32_t rest = count - 32u;
+        uint32_t moved = 0;
+        if (lane < rest) moved = st.slot[row][32u + lane];
+        __syncwarp();
+        if (lane < rest) st.slot[row][lane] = moved;
+        count = rest;
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& st, uint32_t count, int row, int queue, uint32_t lane) {
+    if (count == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&A.counters[queue], (unsigned long long)count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < count) wf_queue(A, queue)[base + lane] = st.slot[row][lane];
+    if (lane + 32u < count) wf_queue(A, queue)[base + 32u + lane] = st.slot[row][lane + 32u];
+}
+
 __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+    __shared__ WfStage stage[4];  // one per warp of the block
     const RenderConstants& rc = LP.rc;
     const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
     const uint32_t n = (uint32_t)A.counters[q_in];
     const uint32_t lane = threadIdx.x & 31u;
+    WfStage& st = stage[threadIdx.x >> 5];
+    uint32_t n_surface = 0, n_metal = 0, n_other = 0, n_regen = 0;  // warp-uniform fill of the staging rows
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n);  // rays = closest-hit queries
     const uint32_t* __restrict__ queue = wf_queue(A, q_in);
     unsigned long long* cursor = &A.counters[WF_CURSOR];
+    uint32_t w_next = 0, w_end = 0;  // warp-uniform: the queue range this warp hands out to its lanes
+    // chunk: a few draws per warp on a full queue, but never so large that a short queue lands on a handful of warps
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t chunk = max(32u, min((uint32_t)WRT_WF_CURSOR_CHUNK, (n / (2u * n_warps)) & ~31u));
     Trav T;
     uint4 stack[WRT_STACK_DEPTH];
-    d3 wo = mk(0, 0, 0), wd = mk(0, 0, 1);
-    double time = 0.0;
     uint32_t slot = 0;
     bool has = false, drained = false;
     T.node = WRT_NONE; T.pc = 0; T.end = 0; T.sp = 0;
     unsigned long long steps = 0;
+    // the world-space ray is only needed again when a pop or a POP op changes the transform context (rare; never in scenes
+    // without instances): it is re-read from the path pool there instead of living in 12 registers
+    auto world_ray = [&](d3& wo, d3& wd, double& time) {
+        const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
+        const double2 a = p[0], b = p[1], c = p[2];
+        wo = mk(a.x, a.y, b.x); wd = mk(b.y, c.x, c.y);
+        time = S.has_moving ? A.paths[slot].time : 0.0;
+    };
     for (;;) {
-        // ---- refill: lanes without a ray draw the next queue entries with one atomic per warp ----
+        // ---- refill: the warp draws WRT_WF_CURSOR_CHUNK queue entries at a time and hands them to the lanes without a ray ----
         const bool want = !has && !drained;
         const unsigned wanting = __ballot_sync(0xffffffffu, want);
         if (wanting) {
-            const int leader = __ffs(wanting) - 1;
-            unsigned long long first = 0;
-            if ((int)lane == leader) first = atomicAdd(cursor, (unsigned long long)__popc(wanting));
-            first = __shfl_sync(0xffffffffu, first, leader);
+            if (w_next >= w_end) {
+                unsigned long long first = 0;
+                if (lane == 0) first = atomicAdd(cursor, (unsigned long long)chunk);
+                first = __shfl_sync(0xffffffffu, first, 0);
+                w_next = (uint32_t)min(first, (unsigned long long)n);
+                w_end = (uint32_t)min(first + chunk, (unsigned long long)n);
+            }
             if (want) {
-                const unsigned long long mine = first + __popc(wanting & ((1u << lane) - 1u));
-                if (mine < n) {
+                const uint32_t mine = w_next + __popc(wanting & ((1u << lane) - 1u));
+                if (mine < w_end) {
                     slot = __ldg(queue + mine);
-                    const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
-                    const double2 a = p[0], b = p[1], c = p[2];
-                    wo = mk(a.x, a.y, b.x); wd = mk(b.y, c.x, c.y);
-                    if (S.has_moving) time = A.paths[slot].time;
+                    d3 wo, wd;
+                    double time;
+                    world_ray(wo, wd, time);
                     trav_init(S, T, wo, wd, time, 1e-4, CUDART_INF);
                     has = true;
-                } else {
-                    drained = true;
+                } else if (w_end >= n) {
+                    drained = true;  // the queue is exhausted (lanes beyond a chunk's end simply ask again next round)
                 }
             }
+            w_next = min(w_next + (uint32_t)__popc(wanting), w_end);
         }
-        if (!__any_sync(0xffffffffu, has)) break;
-        // ---- node phase: binary32 child-pair records, while at least half of the lanes that hold a ray stand on one ----
+        if (!__any_sync(0xffffffffu, has)) {
+            if (__all_sync(0xffffffffu, drained)) break;
+            continue;
+        }
+        // ---- node phase: box records, while at least half of the lanes that hold a ray stand on one ----
         const int n_has = __popc(__ballot_sync(0xffffffffu, has));
 #pragma unroll 1
         for (int k = 0; k < WRT_WF_NODE_BURST; ++k) {
@@ -1171,9 +1230,9 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
         for (int k = 0; k < WRT_WF_LEAF_BURST; ++k) {
             const bool in_leaf = has && !done && T.node == WRT_NONE;
             if (!__any_sync(0xffffffffu, in_leaf)) break;
-            if (in_leaf) { done = trav_leaf_step(S, T, stack, wo, wd, time, 1e-4, CUDART_INF); ++steps; }
+            if (in_leaf) { done = trav_leaf_step_lazy(S, T, stack, world_ray, 1e-4, CUDART_INF); ++steps; }
         }
-        // ---- retire finished rays (warp-uniform: the queue appends are ballots) ----
+        // ---- retire finished rays (warp-uniform: the staging appends are ballots) ----
         const bool fin = has && done;
         if (__any_sync(0xffffffffu, fin)) {
             int route = -1;
@@ -1192,12 +1251,16 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
                 }
                 has = false;
             }
-            wf_push(A, WQ_SURFACE, route == WQ_SURFACE, slot);
-            wf_push(A, WQ_METAL, route == WQ_METAL, slot);
-            wf_push(A, WQ_OTHER, route == WQ_OTHER, slot);
-            wf_push(A, q_regen, regen, slot);
+            wf_stage_push(A, st, n_surface, 0, WQ_SURFACE, route == WQ_SURFACE, slot, lane);
+            wf_stage_push(A, st, n_metal, 1, WQ_METAL, route == WQ_METAL, slot, lane);
+            wf_stage_push(A, st, n_other, 2, WQ_OTHER, route == WQ_OTHER, slot, lane);
+            wf_stage_push(A, st, n_regen, 3, q_regen, regen, slot, lane);
         }
     }
+    wf_stage_flush(A, st, n_surface, 0, WQ_SURFACE, lane);
+    wf_stage_flush(A, st, n_metal, 1, WQ_METAL, lane);
+    wf_stage_flush(A, st, n_other, 2, WQ_OTHER, lane);
+    wf_stage_flush(A, st, n_regen, 3, q_regen, lane);
     for (int off = 16; off > 0; off >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, off);
     if (lane == 0 && steps) atomicAdd(&A.counters[WF_STEPS], steps);
 }

@@ -724,6 +724,8 @@ struct Compiler {
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
         rebuild_trees();
         build_nodes4();
+        const char* force_wide = std::getenv("WRT_WIDE_TREE");  // A/B switch: 0 / 1 overrides the size rule
+        out.use_wide = force_wide ? (force_wide[0] == '1') : (out.nodes2.size() >= WRT_WIDE_TREE_MIN_RECORDS);
         prune_program();
         // transform chains in application order (outermost first), so the device needs no per-thread array
         out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
@@ -871,7 +873,7 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
 namespace {
 uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi);
 uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard) {
-#if WRT_WIDE_TREE
+  if (cs.use_wide) {
     if (rec >= cs.nodes4.size() || guard > 4096) return 1u << 20;  // malformed: never fits
     const Node4& r = cs.nodes4[rec];
     uint32_t need = 0, n_children = 0;
@@ -882,7 +884,7 @@ uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard
         need = std::max(need, c);
     }
     return need + (n_children ? n_children - 1 : 0u);  // the other children wait on the stack while one is descended
-#else
+  } else {
     if (rec >= cs.nodes2.size() || guard > 4096) return 1u << 20;  // malformed: never fits
     const Node2& r = cs.nodes2[rec];
     uint32_t need = 0;
@@ -894,14 +896,14 @@ uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard
     }
     const bool two = r.l_desc != WRT_NONE && r.r_desc != WRT_NONE;
     return need + (two ? 1u : 0u);  // the other child waits on the stack while this one is descended
-#endif
+  }
 }
 uint32_t stack_need_range(const CompiledScene& cs, uint32_t lo, uint32_t hi) {
     uint32_t need = 0;
     for (uint32_t pc = lo; pc < hi && pc < cs.ops.size();) {
         const uint4 op = cs.ops[pc];
         if (op.x == OP_NODE) {  // nested tree: the rest of the range waits while it is descended
-            const uint32_t root = WRT_WIDE_TREE ? (op.y < cs.root4.size() ? cs.root4[op.y] : WRT_NONE) : op.y;
+            const uint32_t root = cs.use_wide ? (op.y < cs.root4.size() ? cs.root4[op.y] : WRT_NONE) : op.y;
             need = std::max(need, 1u + stack_need_record(cs, root, 0));
             pc = op.z > pc ? op.z : pc + 1;
         } else {

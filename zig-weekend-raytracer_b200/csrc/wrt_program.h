@@ -16,6 +16,7 @@ struct CompiledScene {
     std::vector<BoxTight> boxes_tight;
     std::vector<Node2> nodes2;  // parallel to boxes_*: child-pair records of the bvh_node ops (ordered traversal)
     std::vector<Node4> nodes4;  // the same trees collapsed to four-wide records (what the ordered traversal walks)
+    bool use_wide = false;        // the ordered traversal walks nodes4 (large trees) instead of nodes2
     std::vector<uint32_t> root4;  // per box index: Node4 record of the tree rooted at that bvh_node op, WRT_NONE otherwise
     std::vector<SphereGeom> spheres;
     std::vector<SphereAux> sphere_aux;  // empty unless a sphere moves
