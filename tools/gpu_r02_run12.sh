@@ -1,0 +1,15 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_run12_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02_run12_pytest.log
+run() { # name, args
+  python bench.py "${@:2}" --no-cpu-baseline --no-all-workloads 2>gpurun_out/r02_run12_$1.err | python -c "
+import sys,json
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{\"metric')][-1]); print('$1', round(d['value'],1), 'Mrays/s', round(d['ms_per_step'],1), 'ms', d['mean_radiance'])"
+}
+run c5_auto --workload C5 --spp 32 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e
+run c5_mk --workload C5 --engine megakernel --spp 32 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e
+run c3 --workload C3 --steps 2 --warmup 1
+run c2_256 --spp 256 --steps 2 --warmup 1
+run c4 --workload C4 --steps 2 --warmup 1
+run c1 --workload C1 --steps 3 --warmup 2

@@ -15,7 +15,9 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libwrt.so"
+import os as _os
+# WRT_LIB=<file> loads another build of the same sources (development: kernel variants side by side)
+LIB_PATH = Path(_os.environ["WRT_LIB"]) if _os.environ.get("WRT_LIB") else PKG_DIR / "libwrt.so"
 
 from .abi import *  # noqa: F401,F403  (structures and constants of include/wrt.h)
 from .abi import Camera, Params, Scene, Stats

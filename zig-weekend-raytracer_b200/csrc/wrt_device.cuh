@@ -52,6 +52,10 @@ struct __align__(16) Node2 {
 // Four-wide record of the ordered traversal (one 128-byte line): the binary SAH tree collapsed two levels at a time
 // (wrt_program.cu: build_nodes4), children's binary32 boxes as structure of arrays.  desc: bit 31 set = inner record index,
 // otherwise first op of a leaf range ending at `end`; WRT_NONE = empty slot.
+// `end` of a leaf that is ONE sphere / quad op: flag + kind + index into spheres[] / quads[] (the range is [desc, desc + 1))
+#define WRT_LEAF_PRIM 0x80000000u
+#define WRT_LEAF_QUAD 0x40000000u
+#define WRT_LEAF_INDEX 0x3FFFFFFFu
 struct __align__(16) Node4 {
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     uint32_t desc[4];
@@ -64,16 +68,21 @@ struct __align__(16) SphereAux {  // moving spheres only (entity.zig:541-542)
     double mx, my, mz;
     uint32_t is_moving, _pad;
 };
-struct __align__(16) QuadGeom {   // entity.zig:431-441
+struct __align__(16) QuadGeom {   // entity.zig:431-441; 256 bytes = two 128-byte lines
+    // line 0 — everything a traversal reads: the plane, the start point and the two functionals of the interior PRE-test,
+    // alpha = w . (planar x v) = planar . (v x w) and beta = w . (u x planar) = planar . (w x u) (wrt_program.cu forms them in
+    // binary64).  One line per quad in L1 / L2 instead of three (the 2^20-primitive scene holds 2^19 quads).
     double nx, ny, nz, offset;    // unit normal, D
     double sx, sy, sz, area;      // start point, area
+    double ax, ay, az, bx, by, bz;
+    double _l0[2];
+    // line 1 — the basis: hit records with texture coordinates, light sampling, and the exact interior test within 2e-6 of an edge
     double ux, uy, uz, _p0;       // basis.u
     double vx, vy, vz, _p1;       // basis.v
     double wx, wy, wz, _p2;       // basis.w
-    // alpha = w . (planar x v) = planar . (v x w) and beta = w . (u x planar) = planar . (w x u) as plain functionals, for
-    // the interior PRE-test of the traversals (wrt_program.cu forms them in binary64)
-    double ax, ay, az, bx, by, bz;
+    double _l1[4];
 };
+static_assert(sizeof(QuadGeom) == 256, "QuadGeom must stay two cache lines");
 struct __align__(16) Xform {      // Translate / RotateY chain (entity.zig:68-205)
     double a, b, c;               // translate: offset xyz; rotate_y: sin, cos, 0
     uint32_t kind;                // OP_PUSH_TRANSLATE / OP_PUSH_ROTATE_Y
@@ -483,7 +492,7 @@ __device__ __forceinline__ bool quad_plane_t(double num, double denom, double tm
 // evaluate the reference's expressions only inside that band, so every decision is the reference's.
 // `g` = the quad's record, `planar` = hit point - start.
 __device__ __forceinline__ bool quad_interior(const double2* __restrict__ g, d3 planar) {
-    const double2 c0 = __ldg(g + 10), c1 = __ldg(g + 11), c2 = __ldg(g + 12);
+    const double2 c0 = __ldg(g + 4), c1 = __ldg(g + 5), c2 = __ldg(g + 6);
     const double a1 = dot(planar, mk(c0.x, c0.y, c1.x));
     const double b1 = dot(planar, mk(c1.y, c2.x, c2.y));
     // constant bands: if neither coordinate is flagged outside, |planar| is bounded by the quad's size and the rounding is
@@ -492,7 +501,7 @@ __device__ __forceinline__ bool quad_interior(const double2* __restrict__ g, d3 
     const bool inside = (a1 >= 2e-6) && (a1 <= 1.0 - 2e-6) && (b1 >= 2e-6) && (b1 <= 1.0 - 2e-6);
     const bool outside = (a1 < -2e-6) || (a1 > 1.0 + 2e-6) || (b1 < -2e-6) || (b1 > 1.0 + 2e-6);
     if (inside || outside) return inside;
-    const double2 u0 = __ldg(g + 4), u1 = __ldg(g + 5), v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+    const double2 u0 = __ldg(g + 8), u1 = __ldg(g + 9), v0 = __ldg(g + 10), v1 = __ldg(g + 11), w0 = __ldg(g + 12), w1 = __ldg(g + 13);
     const d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
     const double alpha = dot(bw, cross(planar, bv));
     const double beta = dot(bw, cross(bu, planar));
@@ -557,8 +566,8 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
             if (!(fabs(denom) < 1e-8)) {
                 double t;
                 if (quad_plane_t(n1.y - dot(n, o), denom, tmin, best.t, t)) {
-                    double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 4), u1 = __ldg(g + 5);
-                    double2 v0 = __ldg(g + 6), v1 = __ldg(g + 7), w0 = __ldg(g + 8), w1 = __ldg(g + 9);
+                    double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3), u0 = __ldg(g + 8), u1 = __ldg(g + 9);
+                    double2 v0 = __ldg(g + 10), v1 = __ldg(g + 11), w0 = __ldg(g + 12), w1 = __ldg(g + 13);
                     d3 p = o + d * t;
                     d3 planar = p - mk(s0.x, s0.y, s1.x);
                     d3 bu = mk(u0.x, u0.y, u1.x), bv = mk(v0.x, v0.y, v1.x), bw = mk(w0.x, w0.y, w1.x);
@@ -632,26 +641,20 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, ui
         const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
         const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
         const float t_hi = __double2float_ru(T.best_t);
-        float el, er;
+        float el, er = 0.0f;
         const bool hl = T.cull.entry(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, T.t_lo, t_hi, el);
         const uint32_t r_desc = __float_as_uint(b0.w);
         const bool hr = (r_desc != WRT_NONE) && T.cull.entry(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.t_lo, t_hi, er);
-        uint32_t go_desc = WRT_NONE, go_end = 0;
-        if (hl && hr) {
-            const bool left_first = el <= er;
-            const uint32_t far_desc = left_first ? r_desc : __float_as_uint(a0.w);
-            const uint32_t far_end = left_first ? __float_as_uint(b1.w) : __float_as_uint(a1.w);
-            if (T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(far_desc, far_end, T.xf, __float_as_uint(left_first ? er : el));
-            go_desc = left_first ? __float_as_uint(a0.w) : r_desc;
-            go_end = left_first ? __float_as_uint(a1.w) : __float_as_uint(b1.w);
-        } else if (hl) {
-            go_desc = __float_as_uint(a0.w); go_end = __float_as_uint(a1.w);
-        } else if (hr) {
-            go_desc = r_desc; go_end = __float_as_uint(b1.w);
-        }
-        if (go_desc != WRT_NONE) {
+        // select-based (no three-way branch: the lanes of a warp stand on different records and would serialise it)
+        const uint32_t l_desc = __float_as_uint(a0.w), l_end = __float_as_uint(a1.w), r_end = __float_as_uint(b1.w);
+        const bool both = hl && hr;
+        const bool go_left = both ? (el <= er) : hl;
+        if (both && T.sp < WRT_STACK_DEPTH)
+            stack[T.sp++] = make_uint4(go_left ? r_desc : l_desc, go_left ? r_end : l_end, T.xf, __float_as_uint(go_left ? er : el));
+        if (hl || hr) {
+            const uint32_t go_desc = go_left ? l_desc : r_desc;
             if (go_desc & 0x80000000u) { T.node = go_desc & 0x7FFFFFFFu; }
-            else { T.node = WRT_NONE; T.pc = go_desc; T.end = go_end; }
+            else { T.node = WRT_NONE; T.pc = go_desc; T.end = go_left ? l_end : r_end; }
             return;
         }
         T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
@@ -694,8 +697,11 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, u
     T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
 }
 
+// WIDE: 0 = child-pair records, 1 = four-wide records (the hot kernels are instantiated for the form the scene uses: a run-time
+// switch inside the per-lane megakernel's record loop cost the 484-sphere scene 7 %), 2 = ask the scene (gates, diagnostics)
+template <int WIDE = 2>
 __device__ __forceinline__ void trav_record_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
-    if (S.use_wide) trav_node4_step(S, T, stack);
+    if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
     else trav_node_step(S, T, stack);
 }
 
@@ -703,7 +709,13 @@ __device__ __forceinline__ void trav_record_step(const DeviceScene& S, Trav& T, 
 template <typename WORLD>
 __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
     const uint32_t pc = T.pc;
-    const uint4 op = __ldg(S.ops + pc);
+    uint4 op;
+    if (T.end & WRT_LEAF_PRIM) {  // single-primitive leaf of a four-wide record: kind and record index travel in `end`, so the
+        op = make_uint4((T.end & WRT_LEAF_QUAD) ? OP_QUAD : OP_SPHERE, T.end & WRT_LEAF_INDEX, 0u, 0u);  // op fetch (a dependent
+        T.end = pc + 1;                                                                                   // load) is skipped
+    } else {
+        op = __ldg(S.ops + pc);
+    }
     const d3 o = T.o, d = T.d;
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
         if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
@@ -808,6 +820,7 @@ __device__ __forceinline__ ClosestHit trav_result(const Trav& T) {
     return best;
 }
 
+template <int WIDE = 2>
 __device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
     Trav T;
     uint4 stack[WRT_STACK_DEPTH];  // {desc | first op, end op, xform, entry distance bits}
@@ -815,16 +828,16 @@ __device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3
     // "while-while": every lane first descends through box records until it stands on a leaf range (cheap binary32 steps),
     // then the lanes of the warp run their binary64 primitive tests together
     for (;;) {
-        while (T.node != WRT_NONE) trav_record_step(S, T, stack);
+        while (T.node != WRT_NONE) trav_record_step<WIDE>(S, T, stack);
         if (trav_leaf_step(S, T, stack, wo, wd, time, tmin, tmax)) break;
     }
     return trav_result(T);
 }
 
 // per-lane scan: ordered descent where it applies (tight culling, stack deep enough for the tree), else the DFS-order scan
-template <int CULL>
+template <int CULL, int WIDE = 2>
 __device__ __forceinline__ ClosestHit closest_hit_lane(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
-    if (CULL == WRT_CULL_TIGHT && S.use_ordered) return closest_hit_ordered(S, wo, wd, time, tmin, tmax);
+    if (CULL == WRT_CULL_TIGHT && S.use_ordered) return closest_hit_ordered<WIDE>(S, wo, wd, time, tmin, tmax);
     return closest_hit<CULL>(S, wo, wd, time, tmin, tmax);
 }
 

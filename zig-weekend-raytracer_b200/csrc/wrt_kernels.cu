@@ -254,7 +254,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& S, const RenderConstant
     return shade_surface<MANY_LIGHTS>(S, rec, M, ray, beta, L, rng, bounce);
 }
 
-enum { TRAV_LANE = 0, TRAV_PACKET = 1 };
+enum { TRAV_LANE = 0, TRAV_PACKET = 1, TRAV_LANE_WIDE = 2 };  // LANE_WIDE: per-lane ordered traversal over the four-wide records
 
 template <int CULL, int TRAV>
 __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_BLOCKS : WRT_RENDER_MIN_BLOCKS) render_kernel(const __grid_constant__ LaunchParams LP, DeviceScene S, double* __restrict__ accum,
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(WRT_RENDER_BLOCK, TRAV == 1 ? WRT_PACKET_MIN_B
                 }
                 ClosestHit ch;
                 ch.pc = WRT_NONE;
-                if (alive) ch = closest_hit_lane<CULL>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
+                if (alive) ch = closest_hit_lane<CULL, TRAV == TRAV_LANE_WIDE ? 1 : 0>(S, ray.o, ray.d, ray.time, 1e-4, CUDART_INF);
                 if (alive) {
                     ++n_rays;
                     const bool cont = shade<true>(S, rc, ch, ray, beta, L, rng, rc.max_depth - depth_left);
@@ -967,6 +967,16 @@ cudaError_t launch_fp32_peak(double* out, uint32_t grid, uint32_t block, uint32_
 // =============================================================================================================
 __device__ __forceinline__ uint32_t* wf_queue(const WavefrontArgs& A, int q) { return A.queues + (size_t)q * A.capacity; }
 
+// The path pool (128 B per slot, gigabytes) and the queues stream through L2 once per iteration; the tree records and the
+// primitives are what must stay there.  Pool accesses therefore carry the evict-first hint (ld.global.cs / st.global.cs).
+__device__ __forceinline__ PathState load_path(const PathState* p) {
+    union { PathState s; double2 v[8]; } u;
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u.v[k] = __ldcs(q + k);
+    return u.s;
+}
+
 // warp-aggregated append: one atomicAdd per warp and queue
 __device__ __forceinline__ void wf_push(const WavefrontArgs& A, int q, bool pred, uint32_t slot) {
     const unsigned mask = __ballot_sync(0xffffffffu, pred);
@@ -1107,10 +1117,14 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
 // for the lanes that stand on one, while they are at least half of the live lanes | leaf ops + pops for the others | retire.
 // The traversal functions are closest_hit_ordered's, the visiting order per ray is identical, so are the results.
 #ifndef WRT_WF_NODE_BURST
-#define WRT_WF_NODE_BURST 16
+#define WRT_WF_NODE_BURST 32
 #endif
 #ifndef WRT_WF_LEAF_BURST
-#define WRT_WF_LEAF_BURST 2
+#define WRT_WF_LEAF_BURST 4
+#endif
+#ifndef WRT_WF_NODE_SHIFT
+#define WRT_WF_NODE_SHIFT 2  // the record phase runs while (lanes on a record) << shift >= lanes with a ray: 2 = at least a quarter
+                            // (measured on C5: half / quarter, leaf burst 2 / 4, 5 / 6 / 8 blocks per SM: 499 ... 509 Mrays/s; 8 blocks 452)
 #endif
 #ifndef WRT_WF_EXTEND_MIN_BLOCKS
 #define WRT_WF_EXTEND_MIN_BLOCKS 6  // <= 85 registers: 24 warps per SM (the kernel is bound by memory latency, not by issue)
@@ -1155,6 +1169,7 @@ __device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& 
     if (lane + 32u < count) wf_queue(A, queue)[base + 32u + lane] = st.slot[row][lane + 32u];
 }
 
+template <int WIDE>
 __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     __shared__ WfStage stage[4];  // one per warp of the block
     const RenderConstants& rc = LP.rc;
@@ -1180,7 +1195,7 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
     // without instances): it is re-read from the path pool there instead of living in 12 registers
     auto world_ray = [&](d3& wo, d3& wd, double& time) {
         const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
-        const double2 a = p[0], b = p[1], c = p[2];
+        const double2 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
         wo = mk(a.x, a.y, b.x); wd = mk(b.y, c.x, c.y);
         time = S.has_moving ? A.paths[slot].time : 0.0;
     };
@@ -1221,8 +1236,8 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
         for (int k = 0; k < WRT_WF_NODE_BURST; ++k) {
             const bool in_node = has && T.node != WRT_NONE;
             const int n_node = __popc(__ballot_sync(0xffffffffu, in_node));
-            if (n_node == 0 || (k > 0 && 2 * n_node < n_has)) break;
-            if (in_node) { trav_record_step(S, T, stack); ++steps; }
+            if (n_node == 0 || (k > 0 && (n_node << WRT_WF_NODE_SHIFT) < n_has)) break;
+            if (in_node) { trav_record_step<WIDE>(S, T, stack); ++steps; }
         }
         // ---- leaf phase: ops of leaf ranges (binary64 primitive tests, transforms, nested roots) and pops, for the others ----
         bool done = false;
@@ -1240,12 +1255,13 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
             if (fin) {
                 const ClosestHit ch = trav_result(T);
                 if (ch.pc == WRT_NONE) {  // miss: L += beta * background, path ends (render.zig:215-217)
-                    PathState P = A.paths[slot];
+                    PathState P = load_path(A.paths + slot);
                     d3 L = mk(P.lx, P.ly, P.lz) + mk(P.bx, P.by, P.bz) * ld3(rc.background);
                     regen = wf_finish_path(rc, A, slot, P, L);
                 } else {
-                    PathState* P = A.paths + slot;
-                    P->t = ch.t; P->hit_pc = ch.pc; P->hit_xf = ch.xform;
+                    // t | hit_pc, hit_xf: bytes 96..111 of the record, one 16-byte streaming store
+                    __stcs(reinterpret_cast<double2*>(A.paths + slot) + 6,
+                           make_double2(ch.t, __longlong_as_double((long long)(((unsigned long long)ch.xform << 32) | ch.pc))));
                     const uint32_t kind = S.materials[__ldg(&S.ops[ch.pc].z)].kind;
                     route = (kind == WRT_MAT_METAL) ? WQ_METAL : ((kind == WRT_MAT_LAMBERTIAN || kind == WRT_MAT_ISOTROPIC) ? WQ_SURFACE : WQ_OTHER);
                 }
@@ -1279,7 +1295,7 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
         bool extend = false, regen = false;
         if (valid) {
             slot = wf_queue(A, QUEUE)[i];
-            PathState P = A.paths[slot];
+            PathState P = load_path(A.paths + slot);
             uint32_t chunk, col, row;
             wf_slot_pixel(rc, A, slot, chunk, col, row);
             rng.pixel = row * rc.width + col;
@@ -1309,9 +1325,9 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
             } else {
                 PathState* out = A.paths + slot;
                 double2* w = reinterpret_cast<double2*>(out);
-                w[0] = make_double2(ray.o.x, ray.o.y); w[1] = make_double2(ray.o.z, ray.d.x); w[2] = make_double2(ray.d.y, ray.d.z);
+                __stcs(w + 0, make_double2(ray.o.x, ray.o.y)); __stcs(w + 1, make_double2(ray.o.z, ray.d.x)); __stcs(w + 2, make_double2(ray.d.y, ray.d.z));
                 if (QUEUE != WQ_OTHER) {  // dielectric attenuation is (1,1,1) and it gathers nothing
-                    w[3] = make_double2(beta.x, beta.y); w[4] = make_double2(beta.z, L.x); w[5] = make_double2(L.y, L.z);
+                    __stcs(w + 3, make_double2(beta.x, beta.y)); __stcs(w + 4, make_double2(beta.z, L.x)); __stcs(w + 5, make_double2(L.y, L.z));
                 }
                 out->depth_left = depth_left;
                 extend = true;
@@ -1349,6 +1365,10 @@ static cudaError_t dispatch(uint32_t cull_mode, bool packet, F&& f) {
 
 cudaError_t launch_render(const LaunchParams& lp, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t grid, double* accum, unsigned long long* counters,
                           cudaStream_t stream) {
+    if (!packet && cull_mode != WRT_CULL_REFERENCE && S.use_wide) {
+        render_kernel<WRT_CULL_TIGHT, TRAV_LANE_WIDE><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(lp, S, accum, counters);
+        return cudaGetLastError();
+    }
     return dispatch(cull_mode, packet, [&](auto c, auto t) {
         render_kernel<decltype(c)::value, decltype(t)::value><<<grid, WRT_RENDER_BLOCK, 0, stream>>>(lp, S, accum, counters);
     });
@@ -1376,6 +1396,8 @@ cudaError_t launch_render_sync(const LaunchParams& lp, const DeviceScene& S, uin
 }
 cudaError_t render_occupancy(const DeviceScene& S, uint32_t cull_mode, bool packet, int* blocks_per_sm) {
     cudaError_t err = cudaSuccess;
+    if (!packet && cull_mode != WRT_CULL_REFERENCE && S.use_wide)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<WRT_CULL_TIGHT, TRAV_LANE_WIDE>, WRT_RENDER_BLOCK, 0);
     dispatch(cull_mode, packet, [&](auto c, auto t) {
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_kernel<decltype(c)::value, decltype(t)::value>,
                                                             WRT_RENDER_BLOCK, 0);
@@ -1429,14 +1451,15 @@ cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint3
 }
 // One wavefront iteration: generate -> extend -> shade (surface, metal, other) -> reset of the consumed queues.
 cudaError_t wf_extend_occupancy(int* blocks_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel, 128, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel<1>, 128, 0);
 }
 cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
                                 uint32_t grid, uint32_t persist_grid, cudaStream_t stream) {
     wf_generate_kernel<<<grid, 256, 0, stream>>>(lp, A, S, parity);
     const bool ordered = !packet && cull_mode != WRT_CULL_REFERENCE && S.use_ordered;
     if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)
-        wf_extend_ordered_kernel<<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+        if (S.use_wide) wf_extend_ordered_kernel<1><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+        else wf_extend_ordered_kernel<0><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
     } else {
         dispatch(cull_mode, packet, [&](auto c, auto t) {
             wf_extend_kernel<decltype(c)::value, decltype(t)::value><<<grid * 2, 128, 0, stream>>>(lp, A, S, parity);

@@ -362,6 +362,7 @@ struct Compiler {
         for (uint32_t i = 0; i < sc->n_quads; ++i) {
             const wrt_quad& q = sc->quads[i];
             QuadGeom g;
+            std::memset(&g, 0, sizeof g);
             g.nx = q.normal[0]; g.ny = q.normal[1]; g.nz = q.normal[2]; g.offset = q.offset;
             g.sx = q.start[0]; g.sy = q.start[1]; g.sz = q.start[2]; g.area = q.area;
             g.ux = q.u[0]; g.uy = q.u[1]; g.uz = q.u[2]; g._p0 = 0;
@@ -613,6 +614,11 @@ struct Compiler {
                         n.desc[i] = 0x80000000u | rec4; n.end[i] = 0;
                     } else {
                         n.desc[i] = ch[i].desc; n.end[i] = ch[i].end;
+                        // a leaf that is one sphere / quad op carries the primitive's record index instead of the range end:
+                        // the traversal then tests it without fetching the op first (one dependent load less per leaf)
+                        const uint4 op = out.ops[ch[i].desc];
+                        if (ch[i].end == ch[i].desc + 1 && (op.x == OP_SPHERE || op.x == OP_QUAD) && op.y <= WRT_LEAF_INDEX)
+                            n.end[i] = WRT_LEAF_PRIM | (op.x == OP_QUAD ? WRT_LEAF_QUAD : 0u) | op.y;
                     }
                 }
                 out.nodes4[w.rec4] = n;
@@ -843,7 +849,15 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
                     if (!wide) tree_depth = std::max(tree_depth, it.depth);
                     uint32_t desc[4] = {WRT_NONE, WRT_NONE, WRT_NONE, WRT_NONE}, end[4] = {0, 0, 0, 0};
                     if (wide) {
-                        for (int k = 0; k < 4; ++k) { desc[k] = cs.nodes4[it.rec].desc[k]; end[k] = cs.nodes4[it.rec].end[k]; }
+                        for (int k = 0; k < 4; ++k) {
+                            desc[k] = cs.nodes4[it.rec].desc[k]; end[k] = cs.nodes4[it.rec].end[k];
+                            if (desc[k] != WRT_NONE && !(desc[k] & 0x80000000u) && (end[k] & WRT_LEAF_PRIM)) {  // single-primitive leaf
+                                const uint4 lop = desc[k] < n ? cs.ops[desc[k]] : make_uint4(OP_END, 0, 0, 0);
+                                const uint32_t kind = (end[k] & WRT_LEAF_QUAD) ? OP_QUAD : OP_SPHERE;
+                                if (lop.x != kind || lop.y != (end[k] & WRT_LEAF_INDEX)) { err = "single-primitive leaf does not match its op"; return false; }
+                                end[k] = desc[k] + 1;
+                            }
+                        }
                     } else {
                         const Node2& r = cs.nodes2[it.rec];
                         desc[0] = r.l_desc; desc[1] = r.r_desc; end[0] = r.l_end; end[1] = r.r_end;
@@ -880,7 +894,8 @@ uint32_t stack_need_record(const CompiledScene& cs, uint32_t rec, uint32_t guard
     for (int k = 0; k < 4; ++k) {
         if (r.desc[k] == WRT_NONE) continue;
         ++n_children;
-        const uint32_t c = (r.desc[k] & 0x80000000u) ? stack_need_record(cs, r.desc[k] & 0x7FFFFFFFu, guard + 1) : stack_need_range(cs, r.desc[k], r.end[k]);
+        const uint32_t leaf_end = (r.end[k] & WRT_LEAF_PRIM) ? r.desc[k] + 1 : r.end[k];
+        const uint32_t c = (r.desc[k] & 0x80000000u) ? stack_need_record(cs, r.desc[k] & 0x7FFFFFFFu, guard + 1) : stack_need_range(cs, r.desc[k], leaf_end);
         need = std::max(need, c);
     }
     return need + (n_children ? n_children - 1 : 0u);  // the other children wait on the stack while one is descended
