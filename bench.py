@@ -205,7 +205,11 @@ def run_cpu(wl, spp_sample, seed, threads=None, lib=None):
 
 def cpu_baseline_record(wl, spp_sample, seed, W, H, depth):
     """The CPU number reported beside the GPU one: the faster of the two builds of the oracle, both stated with their flags."""
-    wl_cpu = dict(wl, n_prims=1 << 14) if wl["key"] == "C5" else wl
+    # C5: the reference's culling visits every leaf (aabb.zig:80-101), so its sample is bounded in primitives AND frame
+    # (2^14 primitives, a quarter of the frame's width and height): ~10 s instead of minutes
+    wl_cpu = dict(wl, n_prims=1 << 14, width=wl["width"] // 4, height=wl["height"] // 4) if wl["key"] == "C5" else wl
+    if wl["key"] == "C5":
+        W, H = wl_cpu["width"], wl_cpu["height"]
     builds = {}
     native = native_oracle()
     for name, lib in (("libwro_native.so", native), ("libwro.so", ROOT / "oracle" / "libwro.so")):
@@ -220,8 +224,8 @@ def cpu_baseline_record(wl, spp_sample, seed, W, H, depth):
     best = max(ok, key=lambda k: ok[k]["value"])
     return {"value": ok[best]["value"], "unit": UNIT, "cores": ok[best]["cores"], "kind": "port", "build": best,
             "flags": ok[best]["flags"], "seconds": ok[best]["seconds"],
-            "sample": f"{spp_sample} of {wl['spp']} spp per pixel over the full {W}x{H} frame, depth {depth}"
-                      + (", 2^14 of 2^20 primitives" if wl["key"] == "C5" else ""),
+            "sample": f"{spp_sample} of {wl['spp']} spp per pixel over the {W}x{H} frame, depth {depth}"
+                      + (", 2^14 of 2^20 primitives, frame reduced 4x per side" if wl["key"] == "C5" else ""),
             "builds": builds,
             "note": "throughput is spp-independent; a full-spp CPU frame time quoted from it is an extrapolation"}
 
@@ -231,10 +235,10 @@ def reference_arm(args, wl):
     if rank != 0:
         return 0
     spp_sample = cpu_sample_spp(wl, args.cpu_sample_spp)
-    if wl["key"] == "C5":
-        wl = dict(wl, n_prims=1 << 14)  # the reference's culling visits every leaf (aabb.zig:80-101): bound the sample
-    sample = (f"{spp_sample} of {wl['spp']} spp per pixel over the full {wl['width']}x{wl['height']} frame, depth {wl['depth']}"
-              + (", 2^14 of 2^20 primitives" if wl["key"] == "C5" else ""))
+    if wl["key"] == "C5":  # the reference's culling visits every leaf (aabb.zig:80-101): bound the sample
+        wl = dict(wl, n_prims=1 << 14, width=wl["width"] // 4, height=wl["height"] // 4)
+    sample = (f"{spp_sample} of {wl['spp']} spp per pixel over the {wl['width']}x{wl['height']} frame, depth {wl['depth']}"
+              + (", 2^14 of 2^20 primitives, frame reduced 4x per side" if wl["key"] == "C5" else ""))
     native = native_oracle()
     lib = native or (ROOT / "oracle" / "libwro.so")
     for _ in range(args.warmup):
@@ -470,7 +474,9 @@ def main():
                      "traffic": (wl["dram_b_per_ray_ncu"] * rays_all / args.steps / n_gpus) if "dram_b_per_ray_ncu" in wl else None,
                      "traffic_unit": "bytes per launch (ncu DRAM bytes per ray x rays of this launch; source in profiles/README.md)",
                      "algorithmic_bytes_per_launch": wl["b_ray"] * rays_all / args.steps / n_gpus,
-                     "kernel": "render_kernel", "kernel_ms_per_launch": kern_ms_max / args.steps,
+                     "kernel": ("wavefront iteration loop (wf_extend_ordered_kernel = 84 % of its GPU time, profiles/README.md)"
+                                if launches_all / args.steps / n_gpus > 16 else "render_kernel"),
+                     "kernel_ms_per_launch": kern_ms_max / args.steps,
                      "algorithmic_bytes_per_ray": wl["b_ray"], "peak_source": peak_src,
                      "note": ("NOMINAL for this workload: the scene is cache-resident (real DRAM traffic is `traffic`, a fraction of a "
                               "percent of the algorithmic bytes), so this is not achieved HBM bandwidth; the binding bound is "

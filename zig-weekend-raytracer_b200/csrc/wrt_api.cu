@@ -54,6 +54,12 @@ uint32_t log2u(uint32_t v) {
 
 }  // namespace
 
+#ifndef WRT_WF_POOL_SLOTS
+#define WRT_WF_POOL_SLOTS (32ull << 20)  // path slots of the wavefront pool (128 B of state + 32 B of queue / job space each)
+#endif
+#ifndef WRT_WF_PIPELINES
+#define WRT_WF_PIPELINES 4u  // independent pipelines the pool is cut into (wrt_kernels.h: WavefrontArgs::shared)
+#endif
 #define CU(call)                                                   \
     do {                                                           \
         cudaError_t e__ = (call);                                  \
@@ -147,8 +153,12 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
     ctx->d_ppm_in.release(); ctx->d_ppm_body.release(); ctx->d_ppm_blocks.release(); ctx->d_ppm_offsets.release();
-    ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_counters.release();
+    ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_slot_job.release(); ctx->d_wf_counters.release();
     if (ctx->h_wf_counters) cudaFreeHost(ctx->h_wf_counters);
+    for (int k = 1; k < WRT_WF_MAX_PIPELINES; ++k) {
+        if (ctx->wf_streams[k]) cudaStreamDestroy(ctx->wf_streams[k]);
+        if (ctx->wf_events[k]) cudaEventDestroy(ctx->wf_events[k]);
+    }
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -482,10 +492,11 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     if (n_samples > 0) {
         uint64_t want, min_chunk;
         if (wavefront) {
-            // pool of ~16M path slots (slot = (sample chunk, pixel), 128 B of state each): a few million rays per launch and
-            // device even when eight GPUs share the frame, so the longest single traversal of a launch stays a small part of it
-            want = ((16ull << 20) + frame_pixels - 1) / frame_pixels;
-            min_chunk = 1;
+            // wavefront: jobs are handed to a pool of WRT_WF_POOL_SLOTS path slots as slots fall free, so they are made small
+            // (2^27 (pixel, chunk) jobs per frame, >= 8 samples each): the pool then stays full until the last few hundred
+            // iterations of a frame, on one GPU or on eight
+            want = ((1ull << 27) + frame_pixels - 1) / frame_pixels;
+            min_chunk = 8;
         } else {
             // 2^25 (pixel, chunk) jobs per frame: a few dozen per resident lane even when 8 GPUs share the frame.  The packet
             // kernel takes jobs per lane and is happy with chunks of 4 samples; the kernels that take jobs per warp wait for
@@ -524,47 +535,92 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     unsigned long long wf_rays = 0, wf_paths = 0;
     if (wavefront && rc.total_jobs > 0) {
-        const uint64_t n_slots64 = (uint64_t)rc.n_chunks * n_pixels64;
-        if (n_slots64 > 0xFFFFFF00ull) return ctx->fail(WRT_E_LIMIT, "wavefront pool exceeds 2^32 slots");
-        const uint32_t n_slots = (uint32_t)n_slots64;
+        // jobs = (chunk, pixel) accumulators; the pool holds at most WRT_WF_POOL_SLOTS of them at a time
+        const uint64_t n_jobs64 = (uint64_t)rc.n_chunks * n_pixels64;
+        if (n_jobs64 > 0xFFFFFF00ull) return ctx->fail(WRT_E_LIMIT, "wavefront: more than 2^32 (pixel, chunk) jobs");
+        uint64_t pool_slots = WRT_WF_POOL_SLOTS;
+        uint32_t n_pipes = WRT_WF_PIPELINES;
+        if (const char* env = std::getenv("WRT_WF_POOL")) {  // development: pool size in units of 2^20 slots
+            const long v = std::atol(env);
+            if (v > 0 && v <= 1024) pool_slots = (uint64_t)v << 20;
+        }
+        if (const char* env = std::getenv("WRT_WF_PIPELINES")) {
+            const long v = std::atol(env);
+            if (v >= 1 && v <= WRT_WF_MAX_PIPELINES) n_pipes = (uint32_t)v;
+        }
+        const uint32_t n_slots = (uint32_t)std::min<uint64_t>(n_jobs64, pool_slots);
+        if (n_slots < 4096u * n_pipes) n_pipes = 1;  // small frames: one pipeline
         CU(ctx->d_wf_paths.ensure(n_slots));
         CU(ctx->d_wf_queues.ensure((size_t)wrt::WQ_COUNT * n_slots));
-        CU(ctx->d_wf_counters.ensure(16));
+        CU(ctx->d_wf_slot_job.ensure(n_slots));
+        CU(ctx->d_wf_counters.ensure(16 * WRT_WF_MAX_PIPELINES + wrt::WS_COUNT));
         if (!ctx->h_wf_counters) CU(cudaMallocHost(&ctx->h_wf_counters, 16 * sizeof(unsigned long long)));
-        wrt::WavefrontArgs A;
-        A.paths = ctx->d_wf_paths.p; A.queues = ctx->d_wf_queues.p; A.counters = ctx->d_wf_counters.p;
-        A.accum = ctx->d_accum.p; A.capacity = n_slots; A.n_pixels = n_pixels;
-        A.sobol_matrices = nullptr;
+        for (uint32_t k = 1; k < n_pipes; ++k)
+            if (!ctx->wf_streams[k]) {
+                CU(cudaStreamCreateWithFlags(&ctx->wf_streams[k], cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&ctx->wf_events[k], cudaEventDisableTiming));
+            }
+        ctx->wf_streams[0] = ctx->stream;
+        unsigned long long* d_shared = ctx->d_wf_counters.p + 16 * WRT_WF_MAX_PIPELINES;
+        const uint32_t* sobol_matrices = nullptr;
         if (sobol_sampler) {
             if (!ctx->d_sobol_matrices.p) {
                 CU(ctx->d_sobol_matrices.ensure(1024 * 52));
                 CU(cudaMemcpyAsync(ctx->d_sobol_matrices.p, ctx->blob.matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice, ctx->stream));
             }
-            A.sobol_matrices = ctx->d_sobol_matrices.p;
+            sobol_matrices = ctx->d_sobol_matrices.p;
         }
-        CU(cudaMemsetAsync(A.counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
-        const uint32_t wf_grid = (uint32_t)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        // the pool is cut into n_pipes pipelines (own slots / queues / counters / stream; shared accumulators, job cursor, tallies)
+        wrt::WavefrontArgs A[WRT_WF_MAX_PIPELINES];
+        uint32_t wf_grid[WRT_WF_MAX_PIPELINES];
+        uint32_t first_slot = 0;
+        for (uint32_t k = 0; k < n_pipes; ++k) {
+            const uint32_t cap = n_slots / n_pipes + (k < n_slots % n_pipes ? 1u : 0u);
+            A[k].paths = ctx->d_wf_paths.p + first_slot;
+            A[k].queues = ctx->d_wf_queues.p + (size_t)wrt::WQ_COUNT * first_slot;
+            A[k].counters = ctx->d_wf_counters.p + 16 * k;
+            A[k].accum = ctx->d_accum.p; A[k].capacity = cap; A[k].n_pixels = n_pixels;
+            A[k].slot_job = ctx->d_wf_slot_job.p + first_slot; A[k].n_jobs = n_jobs64;
+            A[k].sobol_matrices = sobol_matrices;
+            A[k].shared = d_shared; A[k].job_base = first_slot;
+            wf_grid[k] = (uint32_t)std::min<uint64_t>((cap + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            first_slot += cap;
+        }
+        CU(cudaMemsetAsync(ctx->d_wf_counters.p, 0, (16 * WRT_WF_MAX_PIPELINES + wrt::WS_COUNT) * sizeof(unsigned long long), ctx->stream));
+        const unsigned long long first_free_job = n_slots;  // jobs [0, n_slots) start in the slots
+        CU(cudaMemcpyAsync(d_shared + wrt::WS_JOB_CURSOR, &first_free_job, sizeof first_free_job, cudaMemcpyHostToDevice, ctx->stream));
         int ext_blocks = 0;
         CU(wrt::wf_extend_occupancy(&ext_blocks));
         const uint32_t persist_grid = (uint32_t)ctx->sm_count * (uint32_t)std::max(ext_blocks, 1);
-        CU(wrt::wf_launch_init(lp, A, wf_grid, ctx->stream));
-        ++launches;
-        // every slot runs chunk_size paths of at most max_depth segments, one segment per iteration
-        const uint64_t max_iters = (uint64_t)rc.chunk_size * p.max_ray_bounce_depth + 8;
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));  // (re-recorded: the pipelines' streams start behind the set-up)
+        for (uint32_t k = 1; k < n_pipes; ++k) CU(cudaStreamWaitEvent(ctx->wf_streams[k], ctx->ev[1], 0));
+        for (uint32_t k = 0; k < n_pipes; ++k) {
+            CU(wrt::wf_launch_init(lp, A[k], wf_grid[k], ctx->wf_streams[k]));
+            ++launches;
+        }
+        // a slot runs at most ceil(jobs / slots) + 1 jobs of chunk_size paths of at most max_depth segments, one segment per
+        // iteration (+ one regeneration step per path)
+        const uint64_t max_iters = ((n_jobs64 + n_slots - 1) / n_slots + 1) * (uint64_t)rc.chunk_size * (p.max_ray_bounce_depth + 1) + 64;
         const uint32_t check_every = 16;
         bool done = false;
         for (uint64_t it = 0; it < max_iters && !done; ++it) {
-            CU(wrt::wf_launch_iteration(lp, A, view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid, persist_grid, ctx->stream));
-            launches += 6;
+            for (uint32_t k = 0; k < n_pipes; ++k) {
+                CU(wrt::wf_launch_iteration(lp, A[k], view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid[k], persist_grid, ctx->wf_streams[k]));
+                launches += 6;
+            }
             if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
-                CU(cudaMemcpyAsync(ctx->h_wf_counters, A.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                for (uint32_t k = 1; k < n_pipes; ++k) {  // the tallies are read behind every pipeline
+                    CU(cudaEventRecord(ctx->wf_events[k], ctx->wf_streams[k]));
+                    CU(cudaStreamWaitEvent(ctx->stream, ctx->wf_events[k], 0));
+                }
+                CU(cudaMemcpyAsync(ctx->h_wf_counters, d_shared, wrt::WS_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
-                done = ctx->h_wf_counters[10] >= n_slots;
+                done = ctx->h_wf_counters[wrt::WS_JOBS_DONE] >= n_jobs64;
             }
         }
         if (!done) return ctx->fail(WRT_E_STATE, "wavefront did not drain within its iteration bound");
-        wf_rays = ctx->h_wf_counters[8];
-        wf_paths = ctx->h_wf_counters[9];
+        wf_rays = ctx->h_wf_counters[wrt::WS_RAYS];
+        wf_paths = ctx->h_wf_counters[wrt::WS_PATHS];
     } else if (rc.total_jobs > 0) {
         if (regroup_engine) CU(wrt::launch_render_regroup(lp, view, p.cull_mode, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
         else if (sync_engine) CU(wrt::launch_render_sync(lp, view, p.cull_mode, packet, grid, ctx->d_accum.p, ctx->d_counters.p, ctx->stream));
@@ -588,7 +644,7 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
     // the lane-job kernel does not count paths: every (pixel, chunk) job runs all its samples
     const bool lane_job_kernel = !wavefront && packet && !sync_engine && !regroup_engine;
     ctx->stats.paths = wavefront ? wf_paths : (lane_job_kernel ? n_pixels64 * n_samples : counters[2]);
-    ctx->stats.traversal_steps = wavefront ? ctx->h_wf_counters[wrt::WF_STEPS] : counters[3];
+    ctx->stats.traversal_steps = wavefront ? ctx->h_wf_counters[wrt::WS_STEPS] : counters[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.kernel_ms = ms_kernel;
     ctx->stats.kernel_ms_min = ctx->stats.kernel_ms_max = ms_kernel;

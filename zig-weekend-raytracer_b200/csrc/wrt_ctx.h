@@ -9,6 +9,8 @@
 #include "wrt_kernels.h"
 #include "wrt_program.h"
 
+#define WRT_WF_MAX_PIPELINES 4
+
 namespace wrt {
 
 template <typename T>
@@ -92,8 +94,11 @@ struct wrt_ctx {
     wrt::DevBuf<unsigned long long> d_counters;
     wrt::DevBuf<wrt::PathState> d_wf_paths;      // wavefront engine: path pool, queues, counters
     wrt::DevBuf<uint32_t> d_wf_queues;
+    wrt::DevBuf<uint32_t> d_wf_slot_job;
     wrt::DevBuf<unsigned long long> d_wf_counters;
     unsigned long long* h_wf_counters = nullptr;  // pinned
+    cudaStream_t wf_streams[WRT_WF_MAX_PIPELINES] = {};  // [0] aliases `stream`
+    cudaEvent_t wf_events[WRT_WF_MAX_PIPELINES] = {};
     uint32_t last_pixels = 0;        // pixels of the last render (this shard)
     bool last_valid = false;
     uint32_t sobol_w = 0, sobol_h = 0;  // resolution lp.sobol was built for

@@ -991,27 +991,39 @@ __device__ __forceinline__ void wf_push(const WavefrontArgs& A, int q, bool pred
 
 __device__ __forceinline__ void wf_slot_pixel(const RenderConstants& rc, const WavefrontArgs& A, uint32_t slot, uint32_t& chunk,
                                               uint32_t& col, uint32_t& row) {
-    chunk = slot / A.n_pixels;
-    const uint32_t local = slot % A.n_pixels;
+    const uint32_t job = A.slot_job[slot];
+    chunk = job / A.n_pixels;
+    const uint32_t local = job % A.n_pixels;
     const uint32_t local_row = local / rc.width;
     col = local % rc.width;
     row = rc.row_shard_index + local_row * rc.row_shard_count;
 }
 
-// A path ended: add it to the slot's colour sum (render.zig:129-135); the slot goes to the regenerate queue if it has
-// samples left.  Returns whether to push to the regenerate queue (the caller does the warp-wide push).
+// A path ended: add it to its job's colour sum (render.zig:129-135).  If the job has samples left the slot regenerates; if
+// not it draws the next job (its first sample regenerates); with no job left the slot retires.  Returns whether to push the
+// slot to the regenerate queue (the caller does the warp-wide push).  Jobs are summed by one slot each, in sample order, so
+// the frame does not depend on which slot ran which job.
 __device__ __forceinline__ bool wf_finish_path(const RenderConstants& rc, const WavefrontArgs& A, uint32_t slot, PathState& P, d3 L) {
     const double scale = 1.0 / (double)rc.spp;
-    double* acc = A.accum + (size_t)slot * 3;
+    const uint32_t job = A.slot_job[slot];
+    double* acc = A.accum + (size_t)job * 3;
     acc[0] += L.x * scale; acc[1] += L.y * scale; acc[2] += L.z * scale;
-    const uint32_t chunk = slot / A.n_pixels;
+    const uint32_t chunk = job / A.n_pixels;
     const uint32_t s_first = rc.sample_begin + chunk * rc.chunk_size;
     const uint32_t s_last = min(s_first + rc.chunk_size, rc.sample_end);
     const uint32_t next = P.sample + 1;
-    A.paths[slot].sample = next;
-    if (next < s_last) return true;
-    atomicAdd(&A.counters[10], 1ull);  // this slot is done (once per slot)
-    return false;
+    if (next < s_last) {
+        A.paths[slot].sample = next;
+        return true;
+    }
+    atomicAdd(&A.shared[WS_JOBS_DONE], 1ull);  // this job is done
+    const unsigned long long next_job = atomicAdd(&A.shared[WS_JOB_CURSOR], 1ull);
+    if (next_job >= A.n_jobs) return false;
+    A.slot_job[slot] = (uint32_t)next_job;
+    double* nacc = A.accum + (size_t)next_job * 3;
+    nacc[0] = 0.0; nacc[1] = 0.0; nacc[2] = 0.0;
+    A.paths[slot].sample = rc.sample_begin + (uint32_t)(next_job / A.n_pixels) * rc.chunk_size;
+    return true;
 }
 
 // iteration parity selects the extend / regenerate queue pair: kernels of iteration `it` read E[it&1], R[it&1] and write
@@ -1019,12 +1031,13 @@ __device__ __forceinline__ bool wf_finish_path(const RenderConstants& rc, const 
 __global__ void __launch_bounds__(256) wf_init_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A) {
     const RenderConstants& rc = LP.rc;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.capacity; slot += gridDim.x * blockDim.x) {
-        const uint32_t chunk = slot / A.n_pixels;
-        A.paths[slot].sample = rc.sample_begin + chunk * rc.chunk_size;  // first sample of the slot (not yet generated)
-        A.accum[(size_t)slot * 3 + 0] = 0.0; A.accum[(size_t)slot * 3 + 1] = 0.0; A.accum[(size_t)slot * 3 + 2] = 0.0;
+        const uint32_t job = A.job_base + slot;  // the pipelines' slots start with the first jobs (sum of capacities <= n_jobs)
+        A.slot_job[slot] = job;
+        A.paths[slot].sample = rc.sample_begin + (job / A.n_pixels) * rc.chunk_size;  // first sample of the job (not yet generated)
+        A.accum[(size_t)job * 3 + 0] = 0.0; A.accum[(size_t)job * 3 + 1] = 0.0; A.accum[(size_t)job * 3 + 2] = 0.0;
         wf_queue(A, WQ_REGEN0)[slot] = slot;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[WQ_REGEN0] = A.capacity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[WQ_REGEN0] = A.capacity;  // (the host sets the shared job cursor)
 }
 
 __global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
@@ -1059,7 +1072,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant_
         wf_push(A, q_out, valid, slot);
     }
     for (int off = 16; off > 0; off >>= 1) started += __shfl_down_sync(0xffffffffu, started, off);
-    if ((threadIdx.x & 31u) == 0 && started) atomicAdd(&A.counters[9], started);
+    if ((threadIdx.x & 31u) == 0 && started) atomicAdd(&A.shared[WS_PATHS], started);
 }
 
 template <int CULL, int TRAV>
@@ -1068,7 +1081,7 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
     const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
     const uint32_t n = (uint32_t)A.counters[q_in];
     const uint32_t n_round = (n + 31u) & ~31u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n);  // rays = closest-hit queries
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.shared[WS_RAYS], (unsigned long long)n);  // rays = closest-hit queries
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool valid = i < n;
         uint32_t slot = 0;
@@ -1178,7 +1191,7 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
     const uint32_t lane = threadIdx.x & 31u;
     WfStage& st = stage[threadIdx.x >> 5];
     uint32_t n_surface = 0, n_metal = 0, n_other = 0, n_regen = 0;  // warp-uniform fill of the staging rows
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n);  // rays = closest-hit queries
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.shared[WS_RAYS], (unsigned long long)n);  // rays = closest-hit queries
     const uint32_t* __restrict__ queue = wf_queue(A, q_in);
     unsigned long long* cursor = &A.counters[WF_CURSOR];
     uint32_t w_next = 0, w_end = 0;  // warp-uniform: the queue range this warp hands out to its lanes
@@ -1278,7 +1291,7 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
     wf_stage_flush(A, st, n_other, 2, WQ_OTHER, lane);
     wf_stage_flush(A, st, n_regen, 3, q_regen, lane);
     for (int off = 16; off > 0; off >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, off);
-    if (lane == 0 && steps) atomicAdd(&A.counters[WF_STEPS], steps);
+    if (lane == 0 && steps) atomicAdd(&A.shared[WS_STEPS], steps);
 }
 
 template <int QUEUE, bool MANY_LIGHTS = false>

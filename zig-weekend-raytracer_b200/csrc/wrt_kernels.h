@@ -50,19 +50,30 @@ struct __align__(16) PathState {  // 128 bytes, one L2 line per slot
 static_assert(sizeof(PathState) == 128, "PathState must stay one cache line");
 
 enum { WQ_EXTEND0 = 0, WQ_EXTEND1, WQ_REGEN0, WQ_REGEN1, WQ_SURFACE, WQ_METAL, WQ_OTHER, WQ_COUNT };
-// counters: [0..WQ_COUNT) queue sizes, [8] rays, [9] paths started, [10] slots finished, [11] read cursor of the persistent
-// extend kernel, [12] traversal steps
-enum { WF_CURSOR = 11, WF_STEPS = 12 };
+// per-pipeline counters: [0..WQ_COUNT) queue sizes, [11] read cursor of the persistent extend kernel
+enum { WF_CURSOR = 11 };
 
 struct WavefrontArgs {
     PathState* paths;
     uint32_t* queues;             // WQ_COUNT arrays of `capacity`
     unsigned long long* counters; // 16 entries
     double* accum;                // [slot][3]
-    uint32_t capacity;            // number of slots
-    uint32_t n_pixels;            // pixels of this shard (slot % n_pixels = local pixel)
+    uint32_t capacity;            // number of slots of the pool
+    uint32_t n_pixels;            // pixels of this shard
     const uint32_t* sobol_matrices;  // WRT_FLAG_SAMPLER_SOBOL: SobolMatrices32 (1024 x 52), else nullptr
+    // A JOB is (sample chunk, pixel of the shard) = one accumulator triple, job = chunk * n_pixels + pixel; a SLOT works
+    // through one job at a time and draws the next one from a counter when its job's samples are done, so the pool stays
+    // full however unevenly the work is spread over the pixels (sky pixels finish their chunk in a few hundred iterations,
+    // pixels deep in the scene need thousands).
+    uint32_t* slot_job;           // [capacity]: the job a slot is working on
+    unsigned long long n_jobs;    // n_chunks * n_pixels
+    // The pool runs as independent PIPELINES (own slots, queues and counters, own stream) that share the accumulators, the job
+    // cursor and the tallies below: while one pipeline's persistent extend kernel drains its last, longest rays — a few
+    // milliseconds during which most of its lanes idle — the other pipeline's kernels fill the SMs.
+    unsigned long long* shared;   // WS_* counters, common to all pipelines
+    uint32_t job_base;            // the jobs this pipeline's slots start with: [job_base, job_base + capacity)
 };
+enum { WS_JOB_CURSOR = 0, WS_JOBS_DONE = 1, WS_RAYS = 2, WS_PATHS = 3, WS_STEPS = 4, WS_COUNT = 8 };
 
 struct LaunchParams;
 cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint32_t grid, cudaStream_t stream);
