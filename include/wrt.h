@@ -237,6 +237,9 @@ typedef struct wrt_stats {
     double gather_ms;        /* device time of the shard gather of the last wrt_group_render (0 otherwise) */
     double kernel_ms_min;    /* min / max of kernel_ms over the devices of a group (== kernel_ms for one device) */
     double kernel_ms_max;
+    double tree_build_ms;    /* time of the ordered traversal's tree build inside the last upload (device events or host wall) */
+    uint32_t tree_build_device; /* 1: the trees were built on the device (wrt_build.cu), 0: on the host threads */
+    uint32_t n_tree_records; /* records of the trees the ordered traversal walks (four-wide or child-pair) */
 } wrt_stats;
 
 typedef struct wrt_ctx wrt_ctx;
@@ -276,6 +279,25 @@ typedef struct wrt_scene_info {
     uint32_t stack_depth;    /* exact worst-case stack use of the ordered traversal on the rebuilt trees */
 } wrt_scene_info;
 WRT_API int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, char* err, size_t err_cap);
+
+/* The tree build on its own (replaces BVHNodeEntity.init, src/entity.zig:226-259, for the ordered traversal): compiles
+ * `scene` and builds the trees over the leaves of every reference BVH — binned surface-area heuristic, then the four-wide
+ * collapse — on CUDA device `cuda_device`, or on the host threads when cuda_device < 0.  Both builders write the same
+ * bytes.  records2 / records4 (may be NULL) receive up to cap2 / cap4 BYTES of the child-pair (64 B) and four-wide (128 B)
+ * records; the counts come back in `info` either way.  wrt_upload_scene runs the same code (device build for scenes of
+ * >= 32768 leaves, WRT_DEVICE_BUILD=0/1 overrides). */
+typedef struct wrt_tree_info {
+    uint32_t n_records2;     /* child-pair records (reference topology records included) */
+    uint32_t n_records4;     /* four-wide records */
+    uint32_t stack_depth;    /* exact worst-case stack use of the ordered traversal */
+    uint32_t use_wide;       /* the ordered traversal walks the four-wide records */
+    uint32_t on_device;      /* where the build ran */
+    uint32_t max_nesting;
+    double build_ms;         /* device events (device build) or host wall time (host build), tree build only */
+    double total_ms;         /* host wall time of the whole call */
+} wrt_tree_info;
+WRT_API int wrt_build_trees(const wrt_scene* scene, int cuda_device, wrt_tree_info* info, void* records2, size_t cap2,
+                    void* records4, size_t cap4, char* err, size_t err_cap);
 
 /* Render (replaces Renderer.render, src/render.zig:29-74) ------------------------------------- */
 /* Host framebuffer: `framebuffer` points at Framebuffer.buffer ([]Color, camera.zig:14); one pixel every

@@ -59,7 +59,9 @@ def test_ctypes_mirror_matches_c_layout(wrt, tmp_path):
                                            "n_lights", "ref_boxes_loose", "stack_depth"]),
         "wrt_stats": (wrt.Stats, ["paths", "rays", "render_ms", "kernel_ms", "upload_ms", "kernel_launches", "program_ops",
                                   "n_prims", "cull_mode_used", "traversal_steps", "ref_boxes_loose", "n_devices", "gather_ms",
-                                  "kernel_ms_min", "kernel_ms_max"]),
+                                  "kernel_ms_min", "kernel_ms_max", "tree_build_ms", "tree_build_device", "n_tree_records"]),
+        "wrt_tree_info": (wrt.TreeInfo, ["n_records2", "n_records4", "stack_depth", "use_wide", "on_device", "max_nesting",
+                                         "build_ms", "total_ms"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, (_, fields) in structs.items():

@@ -60,3 +60,28 @@ def test_invalid_scenes_are_rejected_with_a_reason(wrt, wro):
     flat.root = good_root
     wrt.check_scene(flat)
     sc.close()
+
+
+def test_host_tree_build_is_deterministic_and_survives_coincident_centroids(wrt, wro):
+    """wrt_build_trees on the host threads (cuda_device < 0): the concurrent first levels do not change the records, and a
+    scene whose spheres share one centroid (no separating plane: the fallback split of wrt_treebuild.cuh) still yields a tree
+    that reaches every primitive once (wrt_check_scene) with a logarithmic depth.  The device builder is compared with these
+    bytes in tests/test_gpu_build.py; without a device it must fail loudly."""
+    import numpy as np
+    sc = wro.OracleScene("synthetic", seed=5, n_prims=40000)
+    flat = sc.flatten()
+    a_info, a2, a4 = wrt.build_trees(flat, -1)
+    b_info, b2, b4 = wrt.build_trees(flat, -1)
+    assert np.array_equal(a2, b2) and np.array_equal(a4, b4)
+    assert a_info.n_records4 > 0 and a_info.n_records2 >= 40000 - 1 and a_info.on_device == 0
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(wrt.WrtError):
+            wrt.build_trees(flat, 0)
+    for i in range(flat.n_spheres):
+        flat.spheres[i].center[0], flat.spheres[i].center[1], flat.spheres[i].center[2] = 1.0, 2.0, 3.0
+        flat.spheres[i].radius = 0.25 + 1e-3 * i
+        flat.spheres[i].is_moving = 0
+    info = wrt.check_scene(flat)
+    assert info.tree_depth <= 64
+    sc.close()

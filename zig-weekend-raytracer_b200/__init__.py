@@ -27,7 +27,7 @@ from .abi import Camera, Params, Scene, Stats
 ABI_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_abi_version", "wrt_upload_scene", "wrt_render",
     "wrt_render_device", "wrt_encode_rgb8", "wrt_primary_hits", "wrt_trace_rays", "wrt_sobol_pixel_samples",
-    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm", "wrt_check_scene",
+    "wrt_sobol_dimension_samples", "wrt_get_stats", "wrt_fp64_issue_peak", "wrt_fp32_issue_peak", "wrt_format_ppm", "wrt_check_scene", "wrt_build_trees",
     "wrt_group_create", "wrt_group_destroy", "wrt_group_last_error", "wrt_group_size", "wrt_group_ctx", "wrt_group_upload_scene",
     "wrt_group_render", "wrt_group_encode_rgb8", "wrt_group_get_stats", "wrt_comm_unique_id", "wrt_comm_init", "wrt_render_sharded",
 ]
@@ -66,6 +66,7 @@ def _load() -> C.CDLL:
     lib.wrt_fp32_issue_peak.argtypes = [vp, vp]
     lib.wrt_format_ppm.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     lib.wrt_check_scene.argtypes = [vp, vp, C.c_char_p, C.c_size_t]
+    lib.wrt_build_trees.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.wrt_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     lib.wrt_group_destroy.argtypes = [vp]
     lib.wrt_group_destroy.restype = None
@@ -98,6 +99,27 @@ def check_scene(scene) -> "SceneInfo":
     if rc != 0:
         raise WrtError(rc, err.value.decode(errors="replace"))
     return info
+
+
+def build_trees(scene, device: int = -1, records: bool = True):
+    """The ordered traversal's tree build on its own (wrt_build_trees): on CUDA device `device`, or on the host threads
+    when device < 0.  Returns (TreeInfo, child-pair records as uint8[n, 64], four-wide records as uint8[n, 128]); the two
+    builders write the same bytes.  Raises WrtError (no CPU fallback for device >= 0)."""
+    import numpy as np
+    info = TreeInfo()
+    err = C.create_string_buffer(512)
+    rc = lib.wrt_build_trees(C.addressof(scene), int(device), C.addressof(info), None, 0, None, 0, err, len(err))
+    if rc != 0:
+        raise WrtError(rc, err.value.decode(errors="replace"))
+    if not records:
+        return info, None, None
+    r2 = np.zeros((info.n_records2, 64), np.uint8)
+    r4 = np.zeros((info.n_records4, 128), np.uint8)
+    rc = lib.wrt_build_trees(C.addressof(scene), int(device), C.addressof(info), r2.ctypes.data_as(C.c_void_p), r2.nbytes,
+                             r4.ctypes.data_as(C.c_void_p), r4.nbytes, err, len(err))
+    if rc != 0:
+        raise WrtError(rc, err.value.decode(errors="replace"))
+    return info, r2, r4
 
 
 def _ptr(a):

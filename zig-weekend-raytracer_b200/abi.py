@@ -105,4 +105,10 @@ class Stats(C.Structure):
                 ("upload_ms", C.c_double), ("kernel_launches", C.c_uint32), ("program_ops", C.c_uint32),
                 ("n_prims", C.c_uint32), ("cull_mode_used", C.c_uint32), ("traversal_steps", C.c_uint64),
                 ("ref_boxes_loose", C.c_uint32), ("n_devices", C.c_uint32), ("gather_ms", C.c_double),
-                ("kernel_ms_min", C.c_double), ("kernel_ms_max", C.c_double)]
+                ("kernel_ms_min", C.c_double), ("kernel_ms_max", C.c_double), ("tree_build_ms", C.c_double),
+                ("tree_build_device", C.c_uint32), ("n_tree_records", C.c_uint32)]
+
+
+class TreeInfo(C.Structure):
+    _fields_ = [("n_records2", C.c_uint32), ("n_records4", C.c_uint32), ("stack_depth", C.c_uint32), ("use_wide", C.c_uint32),
+                ("on_device", C.c_uint32), ("max_nesting", C.c_uint32), ("build_ms", C.c_double), ("total_ms", C.c_double)]

@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",          # binary64 ops stay unfused in source order; culling uses explicit fma()
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread",
+    "-Xcompiler", "-ffp-contract=off",  # host side of the same rule (the host and device tree builders must agree bit for bit)
     "--expt-relaxed-constexpr",
 ]
 
@@ -44,8 +45,8 @@ def _newer(target: Path, sources) -> bool:
 def build_wrt(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
     """Each .cu is compiled to its own object (in parallel, only when it or a header changed), then linked."""
     from concurrent.futures import ThreadPoolExecutor
-    cu = [CSRC / "wrt_api.cu", CSRC / "wrt_kernels.cu", CSRC / "wrt_program.cu", CSRC / "wrt_multi.cu"]
-    hdrs = [CSRC / "wrt_device.cuh", CSRC / "wrt_kernels.h", CSRC / "wrt_program.h", CSRC / "wrt_ctx.h", ROOT / "include" / "wrt.h",
+    cu = [CSRC / "wrt_api.cu", CSRC / "wrt_kernels.cu", CSRC / "wrt_program.cu", CSRC / "wrt_multi.cu", CSRC / "wrt_build.cu"]
+    hdrs = [CSRC / "wrt_device.cuh", CSRC / "wrt_treebuild.cuh", CSRC / "wrt_kernels.h", CSRC / "wrt_program.h", CSRC / "wrt_ctx.h", ROOT / "include" / "wrt.h",
             Path(__file__)]
     blob_deps = [CSRC / "wrt_sobol_blob.c", DATA / "sobol_tables.bin", Path(__file__)]
     objs = [c.with_suffix(".o") for c in cu]

@@ -99,6 +99,54 @@ extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, cha
     return WRT_OK;
 }
 
+extern "C" int wrt_build_trees(const wrt_scene* scene, int cuda_device, wrt_tree_info* info, void* records2, size_t cap2, void* records4,
+                               size_t cap4, char* err, size_t err_cap) {
+    auto report = [&](const std::string& msg) {
+        if (err && err_cap) { std::snprintf(err, err_cap, "%s", msg.c_str()); }
+    };
+    if (err && err_cap) err[0] = 0;
+    if (!scene || !info) { report("scene / info is NULL"); return WRT_E_INVALID; }
+    try {
+        const auto t0 = std::chrono::steady_clock::now();
+        wrt::CompiledScene cs;
+        std::string msg;
+        int rc = wrt::compile_scene(scene, cs, msg, /*defer_trees=*/true);
+        if (rc != WRT_OK) { report(msg); return rc; }
+        std::memset(info, 0, sizeof *info);
+        if (cuda_device >= 0) {
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess || cuda_device >= count) {
+                report("wrt_build_trees: no such CUDA device (the device build has no CPU fallback; pass cuda_device < 0 for the host build)");
+                return WRT_E_CUDA;
+            }
+            NvtxRange range("wrt_build_trees: device");
+            rc = wrt::build_trees_device(cs, cuda_device, msg, &info->build_ms);
+            if (rc != WRT_OK) { report(msg); return rc; }
+            info->on_device = 1;
+        } else {
+            NvtxRange range("wrt_build_trees: host");
+            const auto t1 = std::chrono::steady_clock::now();
+            wrt::build_trees_host(cs);
+            info->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        }
+        info->n_records2 = (uint32_t)cs.nodes2.size();
+        info->n_records4 = (uint32_t)cs.nodes4.size();
+        info->stack_depth = cs.stack_depth;
+        info->use_wide = cs.use_wide ? 1u : 0u;
+        info->max_nesting = cs.max_nesting;
+        if (records2 && cap2) std::memcpy(records2, cs.nodes2.data(), std::min(cap2, cs.nodes2.size() * sizeof(wrt::Node2)));
+        if (records4 && cap4) std::memcpy(records4, cs.nodes4.data(), std::min(cap4, cs.nodes4.size() * sizeof(wrt::Node4)));
+        info->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return WRT_OK;
+    } catch (const std::bad_alloc&) {
+        report("wrt_build_trees: out of host memory");
+        return WRT_E_NOMEM;
+    } catch (const std::exception& e) {
+        report(std::string("wrt_build_trees: ") + e.what());
+        return WRT_E_INVALID;
+    }
+}
+
 extern "C" const char* wrt_last_error(const wrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int wrt_create(int cuda_device, wrt_ctx** out) {
@@ -310,13 +358,19 @@ extern "C" int wrt_upload_scene(wrt_ctx* ctx, const wrt_scene* scene) {
     std::string err;
     wrt::CompiledScene cs;  // host arrays live only for the duration of the upload
     int rc;
+    double tree_ms = 0.0;
+    bool tree_on_device = false;
     {
-        NvtxRange range("wrt_upload_scene: compile");
-        rc = wrt::compile_scene(scene, cs, err);
+        NvtxRange range("wrt_upload_scene: compile + tree build");
+        rc = wrt::compile_scene_for_device(scene, cs, err, ctx->device, &tree_ms, &tree_on_device);
     }
     if (rc != WRT_OK) return ctx->fail(rc, "wrt_upload_scene: " + err);
     const double compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return wrt::upload_compiled(ctx, cs, scene, compile_ms);
+    rc = wrt::upload_compiled(ctx, cs, scene, compile_ms);
+    ctx->stats.tree_build_ms = tree_ms;
+    ctx->stats.tree_build_device = tree_on_device ? 1u : 0u;
+    ctx->stats.n_tree_records = (uint32_t)(cs.use_wide ? cs.nodes4.size() : cs.nodes2.size());
+    return rc;
 }
 
 // Build this context's Sobol rows (LaunchParams::sobol) for a W x H framebuffer (scale = ceilPowerOfTwo(max(W,H)), sampler.zig:188).

@@ -282,9 +282,11 @@ extern "C" int wrt_group_upload_scene(wrt_group* g, const wrt_scene* scene) {
         wrt::CompiledScene cs;  // compiled once, copied to every device
         std::string err;
         int rc;
+        double tree_ms = 0.0;
+        bool tree_on_device = false;
         {
-            NvtxRange range("wrt_group_upload_scene: compile");
-            rc = wrt::compile_scene(scene, cs, err);
+            NvtxRange range("wrt_group_upload_scene: compile + tree build");
+            rc = wrt::compile_scene_for_device(scene, cs, err, g->ctx[0]->device, &tree_ms, &tree_on_device);
         }
         if (rc != WRT_OK) return g->fail(rc, "wrt_group_upload_scene: " + err);
         const double compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -296,6 +298,11 @@ extern "C" int wrt_group_upload_scene(wrt_group* g, const wrt_scene* scene) {
         for (auto& t : threads) t.join();
         for (size_t i = 0; i < n; ++i)
             if (rcs[i] != WRT_OK) return g->fail(rcs[i], "wrt_group_upload_scene: device " + std::to_string(g->ctx[i]->device) + ": " + g->ctx[i]->err);
+        for (size_t i = 0; i < n; ++i) {
+            g->ctx[i]->stats.tree_build_ms = tree_ms;
+            g->ctx[i]->stats.tree_build_device = tree_on_device ? 1u : 0u;
+            g->ctx[i]->stats.n_tree_records = (uint32_t)(cs.use_wide ? cs.nodes4.size() : cs.nodes2.size());
+        }
         return WRT_OK;
     } catch (const std::bad_alloc&) {
         return g->fail(WRT_E_NOMEM, "wrt_group_upload_scene: out of host memory");

@@ -7,7 +7,9 @@
 //     recomputed from the primitives in the node's local space (for WRT_CULL_TIGHT);
 //   * primitive ids = first-visit DFS order.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -17,6 +19,7 @@
 #include <system_error>
 
 #include "wrt_program.h"
+#include "wrt_treebuild.cuh"
 
 namespace wrt {
 namespace {
@@ -180,10 +183,7 @@ struct Compiler {
 
     // ---- program emission ------------------------------------------------------------------------------
     uint32_t nest = 0;  // current nesting of bvh_node / instance ops (bounds the ordered traversal's stack)
-    struct BvhItem { uint32_t start, end; Box3 box; };                       // a leaf entity of a reference BVH: its op range + tight box
-    struct BvhRoot { uint32_t record; uint32_t nest; std::vector<BvhItem> items; };
-    std::vector<BvhItem>* cur_items = nullptr;  // != null while emitting below a bvh_node
-    std::vector<BvhRoot> bvh_roots;             // every reference BVH, for rebuild_trees()
+    std::vector<TreeItem>* cur_items = nullptr;  // != null while emitting below a bvh_node; out.tree_inputs collects every reference BVH
     bool emit(uint32_t id, uint32_t xf, uint32_t xf_depth) {
         if (!check_entity(id, "emit")) return false;
         struct Nest { uint32_t& n; uint32_t& mx; bool on; Nest(uint32_t& n_, uint32_t& mx_, bool on_) : n(n_), mx(mx_), on(on_) { if (on) { ++n; if (n > mx) mx = n; } } ~Nest() { if (on) --n; } };
@@ -222,19 +222,21 @@ struct Compiler {
                 const uint32_t box = push_box(e, tb);
                 const size_t at = out.ops.size();
                 out.ops.push_back(make_uint4(OP_NODE, box, 0, 0));
-                // the leaf entities below this BVH's root are collected for rebuild_trees()
+                // the leaf entities below this BVH's root are collected for the tree build (out.tree_inputs)
                 const bool is_root = (cur_items == nullptr);
-                std::vector<BvhItem> root_items;
+                std::vector<TreeItem> root_items;
                 if (is_root) cur_items = &root_items;
                 auto emit_child = [&](uint32_t child) -> bool {
                     if (!check_entity(child, "bvh_node child")) return false;
                     if (sc->entities[child].kind == WRT_ENT_BVH_NODE) return emit(child, xf, xf_depth);
-                    std::vector<BvhItem>* const items = cur_items;
+                    std::vector<TreeItem>* const items = cur_items;
                     cur_items = nullptr;  // a BVH nested inside this leaf (instance, collection) is a tree of its own
-                    BvhItem it;
+                    TreeItem it;
+                    Box3 ib;
                     it.start = (uint32_t)out.ops.size();
-                    const bool child_ok = emit(child, xf, xf_depth) && tight_box(child, it.box);
+                    const bool child_ok = emit(child, xf, xf_depth) && tight_box(child, ib);
                     it.end = (uint32_t)out.ops.size();
+                    for (int k = 0; k < 3; ++k) { it.mn[k] = ib.mn[k]; it.mx[k] = ib.mx[k]; }
                     cur_items = items;
                     if (child_ok) items->push_back(it);
                     return child_ok;
@@ -248,7 +250,7 @@ struct Compiler {
                 out.ops[at].z = end;
                 if (is_root) {
                     cur_items = nullptr;
-                    if (ok) bvh_roots.push_back(BvhRoot{box, nest, std::move(root_items)});
+                    if (ok) out.tree_inputs.push_back(TreeInput{box, nest, std::move(root_items)});
                 }
                 if (ok) {  // child-pair record for the ordered traversal: both children's boxes + where they live in the program
                     Node2 n2;
@@ -416,222 +418,6 @@ struct Compiler {
         return true;
     }
 
-    // ---- ordered-traversal trees ------------------------------------------------------------------------
-    // The ordered traversal (wrt_device.cuh, Trav) only needs SOME binary tree over the leaf entities of each reference
-    // BVH: closest hit and tie rule are properties of the primitives and their DFS positions, not of the tree.  The
-    // reference splits at the median of a RANDOM axis (entity.zig:226-259); here each BVH is rebuilt over the same leaves
-    // with a binned surface-area heuristic on the tight boxes (3 axes x 16 bins, median fallback, depth-capped), which
-    // roughly halves the nodes a ray visits on the 2^20-primitive scene.  `ops`, the reference boxes and everything
-    // WRT_CULL_REFERENCE reads keep the reference topology.  WRT_REFERENCE_TREE=1 keeps it for the ordered traversal too.
-    static double half_area(const Box3& b) {
-        if (!b.valid()) return 0.0;
-        const double dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
-        return dx * dy + dy * dz + dz * dx;
-    }
-    static void set_child(Node2& n, bool left, const Box3& b, uint32_t desc, uint32_t end) {
-        const BoxTight p = padded(b);
-        if (left) {
-            n.lmin[0] = p.min_x; n.lmin[1] = p.min_y; n.lmin[2] = p.min_z; n.l_desc = desc;
-            n.lmax[0] = p.max_x; n.lmax[1] = p.max_y; n.lmax[2] = p.max_z; n.l_end = end;
-        } else {
-            n.rmin[0] = p.min_x; n.rmin[1] = p.min_y; n.rmin[2] = p.min_z; n.r_desc = desc;
-            n.rmax[0] = p.max_x; n.rmax[1] = p.max_y; n.rmax[2] = p.max_z; n.r_end = end;
-        }
-    }
-    // builds the subtree over items[lo, hi) (hi - lo >= 2) into record `rec`; its other hi - lo - 2 records are
-    // nodes2[free, free + hi - lo - 2) (left subtree first), so the layout does not depend on which thread builds what and
-    // large subtrees of the first levels are built concurrently.  Returns the subtree's depth in records.
-    uint32_t build_sah(std::vector<BvhItem>& items, size_t lo, size_t hi, uint32_t rec, uint32_t level, uint32_t free) {
-        constexpr int kBins = 16;
-        auto centroid = [](const BvhItem& it, int k) { return it.box.valid() ? 0.5 * (it.box.mn[k] + it.box.mx[k]) : 0.0; };
-        Box3 cb;
-        cb.reset();
-        for (size_t i = lo; i < hi; ++i) { double c[3] = {centroid(items[i], 0), centroid(items[i], 1), centroid(items[i], 2)}; cb.grow(c); }
-        size_t mid = lo;
-        double best_cost = std::numeric_limits<double>::infinity();
-        int best_axis = -1, best_bin = 0;
-        if (level <= 30) {
-            for (int axis = 0; axis < 3; ++axis) {
-                const double ext = cb.mx[axis] - cb.mn[axis];
-                if (!(ext > 0.0)) continue;
-                Box3 bin_box[kBins];
-                size_t bin_n[kBins] = {};
-                for (auto& b : bin_box) b.reset();
-                const double scale = kBins / ext;
-                for (size_t i = lo; i < hi; ++i) {
-                    int b = (int)((centroid(items[i], axis) - cb.mn[axis]) * scale);
-                    b = std::min(std::max(b, 0), kBins - 1);
-                    ++bin_n[b];
-                    if (items[i].box.valid()) bin_box[b].grow(items[i].box);
-                }
-                double right_area[kBins];
-                size_t right_n[kBins];
-                Box3 acc;
-                acc.reset();
-                size_t n = 0;
-                for (int b = kBins - 1; b > 0; --b) { acc.grow(bin_box[b]); n += bin_n[b]; right_area[b] = half_area(acc); right_n[b] = n; }
-                acc.reset();
-                n = 0;
-                for (int b = 0; b + 1 < kBins; ++b) {  // split after bin b
-                    acc.grow(bin_box[b]);
-                    n += bin_n[b];
-                    if (n == 0 || right_n[b + 1] == 0) continue;
-                    const double cost = half_area(acc) * (double)n + right_area[b + 1] * (double)right_n[b + 1];
-                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
-                }
-            }
-        }
-        if (best_axis >= 0) {
-            const double ext = cb.mx[best_axis] - cb.mn[best_axis];
-            const double scale = kBins / ext, base = cb.mn[best_axis];
-            auto it = std::partition(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)hi, [&](const BvhItem& x) {
-                int b = (int)((centroid(x, best_axis) - base) * scale);
-                b = std::min(std::max(b, 0), kBins - 1);
-                return b <= best_bin;
-            });
-            mid = (size_t)(it - items.begin());
-        }
-        if (mid == lo || mid == hi) {  // no usable SAH split (coincident centroids, depth cap): median of the widest axis
-            int axis = 0;
-            for (int k = 1; k < 3; ++k) if (cb.mx[k] - cb.mn[k] > cb.mx[axis] - cb.mn[axis]) axis = k;
-            mid = lo + (hi - lo) / 2;
-            std::nth_element(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)mid, items.begin() + (ptrdiff_t)hi,
-                             [&](const BvhItem& a, const BvhItem& b) { return centroid(a, axis) < centroid(b, axis); });
-        }
-        Node2 n;
-        std::memset(&n, 0, sizeof n);
-        uint32_t child_rec[2] = {WRT_NONE, WRT_NONE}, child_free[2] = {free, free};
-        uint32_t next = free;
-        for (int side = 0; side < 2; ++side) {
-            const size_t a = side == 0 ? lo : mid, b = side == 0 ? mid : hi;
-            Box3 bb;
-            bb.reset();
-            for (size_t i = a; i < b; ++i) if (items[i].box.valid()) bb.grow(items[i].box);
-            if (b - a == 1) {
-                set_child(n, side == 0, bb, items[a].start, items[a].end);
-            } else {
-                child_rec[side] = next;
-                child_free[side] = next + 1;
-                next += (uint32_t)(b - a - 1);
-                set_child(n, side == 0, bb, 0x80000000u | child_rec[side], 0);
-            }
-        }
-        out.nodes2[rec] = n;
-        uint32_t depth_l = 0, depth_r = 0;
-        const bool fork = level <= 4 && child_rec[0] != WRT_NONE && child_rec[1] != WRT_NONE && (mid - lo) >= 8192 && (hi - mid) >= 8192;
-        bool forked = false;
-        if (fork) {
-            std::future<uint32_t> left;
-            try {
-                left = std::async(std::launch::async, [&] { return build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]); });
-                forked = true;
-            } catch (const std::system_error&) {  // no thread to be had: build this level serially
-                forked = false;
-            }
-            if (forked) {
-                depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
-                depth_l = left.get();
-            }
-        }
-        if (!forked) {
-            if (child_rec[0] != WRT_NONE) depth_l = build_sah(items, lo, mid, child_rec[0], level + 1, child_free[0]);
-            if (child_rec[1] != WRT_NONE) depth_r = build_sah(items, mid, hi, child_rec[1], level + 1, child_free[1]);
-        }
-        return 1 + std::max(depth_l, depth_r);
-    }
-    void rebuild_trees() {
-        const char* keep = std::getenv("WRT_REFERENCE_TREE");
-        if (keep && keep[0] == '1') return;
-        for (BvhRoot& r : bvh_roots) {
-            if (r.items.size() < 2) continue;  // a single leaf: the reference's record is already minimal
-            const uint32_t free = (uint32_t)out.nodes2.size();
-            Node2 none;
-            std::memset(&none, 0, sizeof none);
-            none.l_desc = none.r_desc = WRT_NONE;
-            out.nodes2.resize(out.nodes2.size() + r.items.size() - 2, none);  // a tree over n leaves has n - 1 records, one is r.record
-            const uint32_t depth = build_sah(r.items, 0, r.items.size(), r.record, 1, free);
-            out.max_nesting = std::max(out.max_nesting, r.nest + depth);
-        }
-    }
-
-    // Four-wide records: every tree of nodes2 (SAH-rebuilt or reference topology) collapsed top-down — a record starts with
-    // the two children of a child-pair record and, while it has a free slot, replaces the inner child with the largest box by
-    // that child's own two children.  Boxes, leaf ranges and therefore the set of primitives reached are those of nodes2;
-    // only the fan-out changes: half the dependent record fetches per ray, one 128-byte line each.
-    struct Child4 { float lo[3], hi[3]; uint32_t desc, end; };
-    static float area4(const Child4& c) {
-        const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
-        return (dx < 0 || dy < 0 || dz < 0) ? 0.0f : dx * dy + dy * dz + dz * dx;
-    }
-    static void children_of(const Node2& n, std::vector<Child4>& out4) {
-        Child4 c;
-        for (int k = 0; k < 3; ++k) { c.lo[k] = n.lmin[k]; c.hi[k] = n.lmax[k]; }
-        c.desc = n.l_desc; c.end = n.l_end;
-        if (c.desc != WRT_NONE) out4.push_back(c);
-        for (int k = 0; k < 3; ++k) { c.lo[k] = n.rmin[k]; c.hi[k] = n.rmax[k]; }
-        c.desc = n.r_desc; c.end = n.r_end;
-        if (c.desc != WRT_NONE) out4.push_back(c);
-    }
-    void build_nodes4() {
-        out.nodes4.clear();
-        out.root4.assign(out.nodes2.size(), WRT_NONE);
-        struct Work { uint32_t rec2, rec4; };
-        std::vector<Work> work;
-        for (const BvhRoot& r : bvh_roots) {
-            out.root4[r.record] = (uint32_t)out.nodes4.size();
-            out.nodes4.emplace_back();
-            work.push_back({r.record, out.root4[r.record]});
-            while (!work.empty()) {
-                const Work w = work.back();
-                work.pop_back();
-                std::vector<Child4> ch;
-                children_of(out.nodes2[w.rec2], ch);
-                for (;;) {  // widen: open the inner child with the largest box while a slot is free
-                    if (ch.size() >= 4) break;
-                    int best = -1;
-                    float best_area = -1.0f;
-                    for (size_t i = 0; i < ch.size(); ++i)
-                        if ((ch[i].desc & 0x80000000u) && area4(ch[i]) > best_area) { best = (int)i; best_area = area4(ch[i]); }
-                    if (best < 0) break;
-                    std::vector<Child4> sub;
-                    children_of(out.nodes2[ch[(size_t)best].desc & 0x7FFFFFFFu], sub);
-                    if (ch.size() - 1 + sub.size() > 4) break;
-                    ch.erase(ch.begin() + best);
-                    ch.insert(ch.end(), sub.begin(), sub.end());
-                }
-                Node4 n;
-                for (int i = 0; i < 4; ++i) {  // empty slot: a box nothing can hit, no child
-                    n.lox[i] = n.loy[i] = n.loz[i] = 1.0f; n.hix[i] = n.hiy[i] = n.hiz[i] = -1.0f;
-                    n.desc[i] = WRT_NONE; n.end[i] = 0;
-                }
-                for (size_t i = 0; i < ch.size(); ++i) {
-                    n.lox[i] = ch[i].lo[0]; n.loy[i] = ch[i].lo[1]; n.loz[i] = ch[i].lo[2];
-                    n.hix[i] = ch[i].hi[0]; n.hiy[i] = ch[i].hi[1]; n.hiz[i] = ch[i].hi[2];
-                    if (ch[i].desc & 0x80000000u) {
-                        const uint32_t rec4 = (uint32_t)out.nodes4.size();
-                        out.nodes4.emplace_back();
-                        work.push_back({ch[i].desc & 0x7FFFFFFFu, rec4});
-                        n.desc[i] = 0x80000000u | rec4; n.end[i] = 0;
-                    } else {
-                        n.desc[i] = ch[i].desc; n.end[i] = ch[i].end;
-                        // a leaf that is one sphere / quad op carries the primitive's record index instead of the range end:
-                        // the traversal then tests it without fetching the op first (one dependent load less per leaf)
-                        const uint4 op = out.ops[ch[i].desc];
-                        if (ch[i].end == ch[i].desc + 1 && (op.x == OP_SPHERE || op.x == OP_QUAD) && op.y <= WRT_LEAF_INDEX)
-                            n.end[i] = WRT_LEAF_PRIM | (op.x == OP_QUAD ? WRT_LEAF_QUAD : 0u) | op.y;
-                    }
-                }
-                out.nodes4[w.rec4] = n;
-            }
-        }
-        if (out.nodes4.empty()) {  // keep the device pointer non-null
-            Node4 n;
-            std::memset(&n, 0, sizeof n);
-            for (int i = 0; i < 4; ++i) n.desc[i] = WRT_NONE;
-            out.nodes4.push_back(n);
-        }
-    }
-
     // The program WRT_CULL_TIGHT scans in packet form (closest_hit_packet): `ops` with the work removed that cannot pay for
     // itself when 32 rays share one program counter.  Tight boxes are conservative, so dropping a box test never changes a
     // result; WRT_CULL_REFERENCE must keep every node (its boxes are not conservative) and scans `ops`.
@@ -725,14 +511,30 @@ struct Compiler {
         tight_state.assign(sc->n_entities, 0);
         prim_id.assign(sc->n_entities, WRT_NONE);
         on_stack.assign(sc->n_entities, 0);
+        const bool trace = std::getenv("WRT_TRACE_BUILD") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        const auto t0 = now();
         if (!compile_materials() || !compile_geometry() || !compile_lights()) return code;
+        const auto t1 = now();
+        {  // size the output arrays once (a hint: shared subtrees are emitted once per use and may exceed it)
+            size_t n_nodes = 0, n_xf = 0;
+            for (uint32_t i = 0; i < sc->n_entities; ++i) {
+                const uint32_t k = sc->entities[i].kind;
+                n_nodes += (k == WRT_ENT_BVH_NODE);
+                n_xf += (k == WRT_ENT_TRANSLATE || k == WRT_ENT_ROTATE_Y);
+            }
+            out.ops.reserve((size_t)sc->n_entities + 2 * n_xf + 16);
+            out.boxes_ref.reserve(n_nodes + n_xf + 1);
+            out.boxes_tight.reserve(n_nodes + n_xf + 1);
+            out.nodes2.reserve(n_nodes + n_xf + 1);
+            out.xforms.reserve(n_xf);
+        }
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
-        rebuild_trees();
-        build_nodes4();
-        const char* force_wide = std::getenv("WRT_WIDE_TREE");  // A/B switch: 0 / 1 overrides the size rule
-        out.use_wide = force_wide ? (force_wide[0] == '1') : (out.nodes2.size() >= WRT_WIDE_TREE_MIN_RECORDS);
+        const auto t2 = now();
         prune_program();
+        if (trace) std::fprintf(stderr, "wrt trace: compile: records %.1f ms, program %.1f ms, prune %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));  // the trees of the ordered traversal are built after run(): build_trees_host / build_trees_device
         // transform chains in application order (outermost first), so the device needs no per-thread array
         out.xform_chains.assign(std::max<size_t>(out.xforms.size(), 1) * WRT_MAX_XFORM_DEPTH, WRT_NONE);
         for (size_t x = 0; x < out.xforms.size(); ++x) {
@@ -756,6 +558,170 @@ struct Compiler {
 };
 
 }  // namespace
+
+// ---- ordered-traversal trees, host build ------------------------------------------------------------------------------
+// The ordered traversal (wrt_device.cuh, Trav) only needs SOME binary tree over the leaf entities of each reference BVH:
+// closest hit and tie rule are properties of the primitives and their DFS positions, not of the tree.  The reference splits
+// at the median of a RANDOM axis (entity.zig:226-259); here each BVH is rebuilt over the same leaves with a binned
+// surface-area heuristic on the tight boxes (wrt_treebuild.cuh), which roughly halves the nodes a ray visits on the
+// 2^20-primitive scene.  `ops`, the reference boxes and everything WRT_CULL_REFERENCE reads keep the reference topology.
+// WRT_REFERENCE_TREE=1 keeps it for the ordered traversal too.  The device builder (wrt_build.cu) produces the same bytes.
+namespace {
+
+struct HostTreeBuilder {
+    CompiledScene& out;
+    explicit HostTreeBuilder(CompiledScene& o) : out(o) {}
+
+    // builds the subtree over items[lo, hi) (hi - lo >= 2) into record `rec`; its other hi - lo - 2 records are
+    // nodes2[free, free + hi - lo - 2) (left subtree first), so the layout does not depend on which thread builds what and
+    // large subtrees of the first levels are built concurrently.  Returns the subtree's depth in records.
+    uint32_t build_sah(std::vector<TreeItem>& items, size_t lo, size_t hi, uint32_t rec, uint32_t level, uint32_t free) {
+        double cmn[3], cmx[3];
+        for (int k = 0; k < 3; ++k) { cmn[k] = INFINITY; cmx[k] = -INFINITY; }
+        for (size_t i = lo; i < hi; ++i)
+            for (int k = 0; k < 3; ++k) { const double c = tb_centroid(items[i], k); cmn[k] = fmin(cmn[k], c); cmx[k] = fmax(cmx[k], c); }
+        double best_cost = INFINITY, best_base = 0.0, best_scale = 0.0;
+        int best_axis = -1, best_bin = 0;
+        if (level <= kTreeSahLevels) {
+            for (int axis = 0; axis < 3; ++axis) {
+                const double ext = cmx[axis] - cmn[axis];
+                if (!(ext > 0.0)) continue;
+                uint32_t bin_n[kTreeBins] = {};
+                double bin_box[kTreeBins * 6];
+                for (int b = 0; b < kTreeBins; ++b)
+                    for (int k = 0; k < 3; ++k) { bin_box[b * 6 + k] = INFINITY; bin_box[b * 6 + 3 + k] = -INFINITY; }
+                const double scale = (double)kTreeBins / ext;
+                for (size_t i = lo; i < hi; ++i) {
+                    const TreeItem& it = items[i];
+                    const int b = tb_bin(tb_centroid(it, axis), cmn[axis], scale);
+                    ++bin_n[b];
+                    if (tb_valid(it.mn, it.mx))
+                        for (int k = 0; k < 3; ++k) { bin_box[b * 6 + k] = fmin(bin_box[b * 6 + k], it.mn[k]); bin_box[b * 6 + 3 + k] = fmax(bin_box[b * 6 + 3 + k], it.mx[k]); }
+                }
+                double cost;
+                int bin;
+                tb_sweep_axis(bin_n, bin_box, cost, bin);
+                if (bin >= 0 && cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = bin; best_base = cmn[axis]; best_scale = scale; }
+            }
+        }
+        size_t mid;
+        if (best_axis >= 0) {
+            auto it = std::stable_partition(items.begin() + (ptrdiff_t)lo, items.begin() + (ptrdiff_t)hi, [&](const TreeItem& x) {
+                return tb_bin(tb_centroid(x, best_axis), best_base, best_scale) <= best_bin;
+            });
+            mid = (size_t)(it - items.begin());
+        } else {
+            mid = lo + (hi - lo) / 2;  // no plane separates the centroids, or the depth cap: halve the current order
+        }
+        Node2 n;
+        std::memset(&n, 0, sizeof n);
+        const TreeChildren ch = tb_children((uint32_t)lo, (uint32_t)mid, (uint32_t)hi, free);
+        for (int side = 0; side < 2; ++side) {
+            const size_t a = side == 0 ? lo : mid, b = side == 0 ? mid : hi;
+            double mn[3], mx[3];
+            for (int k = 0; k < 3; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+            for (size_t i = a; i < b; ++i)
+                if (tb_valid(items[i].mn, items[i].mx))
+                    for (int k = 0; k < 3; ++k) { mn[k] = fmin(mn[k], items[i].mn[k]); mx[k] = fmax(mx[k], items[i].mx[k]); }
+            float flo[3], fhi[3];
+            tb_padded(mn, mx, flo, fhi);
+            if (b - a == 1) tb_set_child(n, side, flo, fhi, items[a].start, items[a].end);
+            else tb_set_child(n, side, flo, fhi, 0x80000000u | ch.rec[side], 0);
+        }
+        out.nodes2[rec] = n;
+        uint32_t depth_l = 0, depth_r = 0;
+        const bool fork = level <= 4 && ch.rec[0] != WRT_NONE && ch.rec[1] != WRT_NONE && (mid - lo) >= 8192 && (hi - mid) >= 8192;
+        bool forked = false;
+        if (fork) {
+            std::future<uint32_t> left;
+            try {
+                left = std::async(std::launch::async, [&] { return build_sah(items, lo, mid, ch.rec[0], level + 1, ch.free[0]); });
+                forked = true;
+            } catch (const std::system_error&) {  // no thread to be had: build this level serially
+                forked = false;
+            }
+            if (forked) {
+                depth_r = build_sah(items, mid, hi, ch.rec[1], level + 1, ch.free[1]);
+                depth_l = left.get();
+            }
+        }
+        if (!forked) {
+            if (ch.rec[0] != WRT_NONE) depth_l = build_sah(items, lo, mid, ch.rec[0], level + 1, ch.free[0]);
+            if (ch.rec[1] != WRT_NONE) depth_r = build_sah(items, mid, hi, ch.rec[1], level + 1, ch.free[1]);
+        }
+        return 1 + std::max(depth_l, depth_r);
+    }
+    void rebuild_trees() {
+        for (TreeInput& r : out.tree_inputs) {
+            if (r.items.size() < 2) continue;  // a single leaf: the reference's record is already minimal
+            const uint32_t free = (uint32_t)out.nodes2.size();
+            Node2 none;
+            std::memset(&none, 0, sizeof none);
+            none.l_desc = none.r_desc = WRT_NONE;
+            out.nodes2.resize(out.nodes2.size() + r.items.size() - 2, none);  // a tree over n leaves has n - 1 records, one is r.record
+            const uint32_t depth = build_sah(r.items, 0, r.items.size(), r.record, 1, free);
+            out.max_nesting = std::max(out.max_nesting, r.nest + depth);
+        }
+    }
+
+    // Four-wide records: every tree of nodes2 (SAH-rebuilt or reference topology) collapsed top-down, breadth first
+    // (wrt_treebuild.cuh): half the dependent record fetches per ray, one 128-byte line each.
+    void build_nodes4() {
+        out.nodes4.clear();
+        out.root4.assign(out.nodes2.size(), WRT_NONE);
+        struct Work { uint32_t rec2, rec4; };
+        std::vector<Work> level, next_level;
+        for (const TreeInput& r : out.tree_inputs) {
+            out.root4[r.record] = (uint32_t)out.nodes4.size();
+            out.nodes4.emplace_back();
+            level.assign(1, Work{r.record, out.root4[r.record]});
+            while (!level.empty()) {
+                next_level.clear();
+                for (const Work& w : level) {
+                    TreeChild4 ch[4];
+                    const int n = tb_widen(out.nodes2.data(), w.rec2, ch);
+                    const uint32_t first_child = (uint32_t)out.nodes4.size();
+                    for (int i = 0; i < n; ++i)
+                        if (ch[i].desc & 0x80000000u) {
+                            next_level.push_back(Work{ch[i].desc & 0x7FFFFFFFu, (uint32_t)out.nodes4.size()});
+                            out.nodes4.emplace_back();
+                        }
+                    out.nodes4[w.rec4] = tb_node4(ch, n, first_child, out.ops.data());
+                }
+                level.swap(next_level);
+            }
+        }
+    }
+};
+
+void finish_trees(CompiledScene& out) {
+    if (out.nodes4.empty()) {  // keep the device pointer non-null
+        Node4 n;
+        std::memset(&n, 0, sizeof n);
+        for (int i = 0; i < 4; ++i) n.desc[i] = WRT_NONE;
+        out.nodes4.push_back(n);
+    }
+    const char* force_wide = std::getenv("WRT_WIDE_TREE");  // A/B switch: 0 / 1 overrides the size rule
+    out.use_wide = force_wide ? (force_wide[0] == '1') : (out.nodes2.size() >= WRT_WIDE_TREE_MIN_RECORDS);
+    out.stack_depth = ordered_stack_depth(out);
+    out.trees_built = true;
+}
+
+}  // namespace
+
+bool keep_reference_trees() {
+    const char* keep = std::getenv("WRT_REFERENCE_TREE");
+    return keep && keep[0] == '1';
+}
+
+void build_trees_host(CompiledScene& out) {
+    HostTreeBuilder b(out);
+    if (!keep_reference_trees()) b.rebuild_trees();
+    b.build_nodes4();
+    finish_trees(out);
+}
+
+void finish_trees_after_device_build(CompiledScene& out) { finish_trees(out); }
 
 namespace {
 
@@ -934,14 +900,14 @@ uint32_t ordered_stack_depth(const CompiledScene& cs) {
     return stack_need_range(cs, 0, (uint32_t)cs.ops.size() - 1);
 }
 
-int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err) {
+int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err, bool defer_trees) {
     // nothing may unwind through the C ABI (a Zig or C caller): allocation failures of the vectors and std::system_error of
     // the concurrent SAH build come back as codes
     try {
         out = CompiledScene();
         Compiler c(scene, out, err);
         const int rc = c.run();
-        if (rc == WRT_OK) out.stack_depth = ordered_stack_depth(out);
+        if (rc == WRT_OK && !defer_trees) build_trees_host(out);
         return rc;
     } catch (const std::bad_alloc&) {
         err = "out of host memory while compiling the scene";

@@ -6,8 +6,16 @@
 #include <vector>
 
 #include "wrt_device.cuh"
+#include "wrt_treebuild.cuh"
 
 namespace wrt {
+
+// the leaf entities of one reference BVH: what the ordered traversal's tree over them is built from
+struct TreeInput {
+    uint32_t record;  // the root's child-pair record (= box index of the bvh_node op)
+    uint32_t nest;    // nesting of the root in the program
+    std::vector<TreeItem> items;
+};
 
 struct CompiledScene {
     std::vector<uint4> ops;
@@ -27,6 +35,8 @@ struct CompiledScene {
     std::vector<Texture> textures;
     std::vector<Light> lights;
     std::vector<BoxTight> light_boxes;  // conservative binary32 box of every light (an empty box for kinds whose pdf is 0)
+    std::vector<TreeInput> tree_inputs;  // per reference BVH, program order; consumed (reordered) by the tree build
+    bool trees_built = false;            // nodes2 / nodes4 / root4 / use_wide / stack_depth are final
     uint32_t n_prims = 0;
     uint32_t max_xform_depth = 0;
     uint32_t max_nesting = 0;  // deepest chain of bvh_node / instance ops
@@ -36,8 +46,22 @@ struct CompiledScene {
     bool has_moving = false;
 };
 
-// Returns WRT_OK or a WRT_E_* code with `err` set.
-int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err);
+// Returns WRT_OK or a WRT_E_* code with `err` set.  With defer_trees the trees of the ordered traversal are left to the
+// caller: build_trees_host (what compile_scene runs otherwise) or build_trees_device, which write the same bytes.
+int compile_scene(const wrt_scene* scene, CompiledScene& out, std::string& err, bool defer_trees = false);
+
+// SAH rebuild of every reference BVH over its leaves + four-wide collapse on the host threads (wrt_program.cu).
+void build_trees_host(CompiledScene& cs);
+// The same build on a CUDA device (wrt_build.cu): level-synchronous binned SAH, then the breadth-first collapse; the
+// records come back into `cs`.  `ms` = device time of the build (events), excluding the transfers.  WRT_OK or a code.
+int build_trees_device(CompiledScene& cs, int device, std::string& err, double* build_ms);
+// true when the size rule (or WRT_DEVICE_BUILD=0/1) asks for the device build of this scene's trees
+bool want_device_build(const CompiledScene& cs);
+// compile_scene + the tree build where it belongs for this scene (device `device` or the host threads); what
+// wrt_upload_scene and wrt_group_upload_scene run.  `tree_ms`: time of the tree build, `on_device`: where it ran.
+int compile_scene_for_device(const wrt_scene* scene, CompiledScene& out, std::string& err, int device, double* tree_ms, bool* on_device);
+bool keep_reference_trees();                            // WRT_REFERENCE_TREE=1
+void finish_trees_after_device_build(CompiledScene& cs);  // use_wide, stack depth, sentinels
 
 // Worst-case number of live stack entries of closest_hit_ordered (wrt_device.cuh) over this scene's trees: a child-pair
 // record defers at most one child while it descends the other, a bvh_node met inside a leaf range defers the rest of the
