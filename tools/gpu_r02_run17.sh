@@ -1,0 +1,12 @@
+#!/bin/bash
+# ray reordering before the persistent extend kernel: off / on, bucket widths
+set -u
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py tests/test_gpu_build.py -m gpu -x -q > gpurun_out/r02_run17_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r02_run17_pytest.log
+run() { python bench.py "${@:2}" --no-cpu-baseline --no-all-workloads 2>gpurun_out/r02_run17_$1.err | python -c "
+import sys,json
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{\"metric')][-1]); print('$1', round(d['value'],1), 'Mrays/s', round(d['ms_per_step'],1), 'ms', d['mean_radiance'], d['gpu_launches'], 'e2e', round(d['e2e']['value'],1))"; }
+WRT_WF_SORT=0 run c5_64_nosort --workload C5 --spp 64 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e
+WRT_WF_SORT=1 run c5_64_sort --workload C5 --spp 64 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e
+WRT_WF_SORT=1 WRT_WF_SORT_SHIFT=9 run c5_64_sort_s9 --workload C5 --spp 64 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e
+WRT_WF_SORT=1 WRT_WF_SORT_SHIFT=11 run c5_64_sort_s11 --workload C5 --spp 64 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e

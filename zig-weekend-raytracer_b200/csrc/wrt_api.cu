@@ -201,6 +201,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
     ctx->d_ppm_in.release(); ctx->d_ppm_body.release(); ctx->d_ppm_blocks.release(); ctx->d_ppm_offsets.release();
+    ctx->d_wf_keys.release(); ctx->d_wf_sort_tmp.release(); ctx->d_wf_sort_hist.release();
     ctx->d_wf_paths.release(); ctx->d_wf_queues.release(); ctx->d_wf_slot_job.release(); ctx->d_wf_counters.release();
     if (ctx->h_wf_counters) cudaFreeHost(ctx->h_wf_counters);
     for (int k = 1; k < WRT_WF_MAX_PIPELINES; ++k) {
@@ -311,6 +312,8 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     // ordered traversal only when its exact worst-case stack use fits (ordered_stack_depth walks the rebuilt trees)
     ds.use_ordered = (cs.stack_depth <= WRT_STACK_DEPTH) ? 1u : 0u;
     ds.use_wide = cs.use_wide ? 1u : 0u;
+    ds.prefetch = 0u;
+    if (const char* env = std::getenv("WRT_TRAV_PREFETCH")) ds.prefetch = (uint32_t)std::atoi(env);
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
     // Large trees: ask L2 to keep the four-wide records (the dependent fetches of every traversal step) in preference to the
@@ -607,6 +610,23 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
         CU(ctx->d_wf_paths.ensure(n_slots));
         CU(ctx->d_wf_queues.ensure((size_t)wrt::WQ_COUNT * n_slots));
         CU(ctx->d_wf_slot_job.ensure(n_slots));
+        // ray reordering before the persistent extend kernel (wrt_kernels.h: WavefrontArgs::keys): on for the large trees it
+        // serves; WRT_WF_SORT=0 switches it off, WRT_WF_SORT_SHIFT overrides the bucket width (ops per bucket = 2^shift)
+        uint32_t sort_shift = 0, sort_buckets = 0;
+        {
+            const char* env = std::getenv("WRT_WF_SORT");
+            const bool on = !packet && ctx->ds.use_wide && !(env && env[0] == '0');
+            if (on) {
+                sort_shift = 0;
+                while ((((uint64_t)ctx->ds.n_ops >> sort_shift) + 1) * 8 > (1u << 18)) ++sort_shift;
+                if (const char* s = std::getenv("WRT_WF_SORT_SHIFT")) sort_shift = std::max<uint32_t>(sort_shift, (uint32_t)std::atoi(s));
+                sort_buckets = (uint32_t)((((uint64_t)ctx->ds.n_ops >> sort_shift) + 1) * 8);
+                CU(ctx->d_wf_keys.ensure(2 * (size_t)n_slots));
+                CU(ctx->d_wf_sort_tmp.ensure(n_slots));
+                CU(ctx->d_wf_sort_hist.ensure((size_t)sort_buckets * WRT_WF_MAX_PIPELINES));
+                CU(cudaMemsetAsync(ctx->d_wf_sort_hist.p, 0, (size_t)sort_buckets * WRT_WF_MAX_PIPELINES * sizeof(uint32_t), ctx->stream));
+            }
+        }
         CU(ctx->d_wf_counters.ensure(16 * WRT_WF_MAX_PIPELINES + wrt::WS_COUNT));
         if (!ctx->h_wf_counters) CU(cudaMallocHost(&ctx->h_wf_counters, 16 * sizeof(unsigned long long)));
         for (uint32_t k = 1; k < n_pipes; ++k)
@@ -637,6 +657,10 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
             A[k].slot_job = ctx->d_wf_slot_job.p + first_slot; A[k].n_jobs = n_jobs64;
             A[k].sobol_matrices = sobol_matrices;
             A[k].shared = d_shared; A[k].job_base = first_slot;
+            A[k].keys = sort_buckets ? ctx->d_wf_keys.p + 2 * (size_t)first_slot : nullptr;
+            A[k].sort_tmp = sort_buckets ? ctx->d_wf_sort_tmp.p + first_slot : nullptr;
+            A[k].sort_hist = sort_buckets ? ctx->d_wf_sort_hist.p + (size_t)k * sort_buckets : nullptr;
+            A[k].sort_buckets = sort_buckets; A[k].sort_shift = sort_shift;
             wf_grid[k] = (uint32_t)std::min<uint64_t>((cap + 255) / 256, (uint64_t)ctx->sm_count * 8);
             first_slot += cap;
         }
@@ -660,7 +684,7 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
         for (uint64_t it = 0; it < max_iters && !done; ++it) {
             for (uint32_t k = 0; k < n_pipes; ++k) {
                 CU(wrt::wf_launch_iteration(lp, A[k], view, p.cull_mode, packet, (uint32_t)(it & 1), wf_grid[k], persist_grid, ctx->wf_streams[k]));
-                launches += 6;
+                launches += sort_buckets ? 10 : 6;
             }
             if ((it + 1) % check_every == 0 || it + 1 == max_iters) {
                 for (uint32_t k = 1; k < n_pipes; ++k) {  // the tallies are read behind every pipeline

@@ -95,6 +95,7 @@ struct wrt_ctx {
     wrt::DevBuf<wrt::PathState> d_wf_paths;      // wavefront engine: path pool, queues, counters
     wrt::DevBuf<uint32_t> d_wf_queues;
     wrt::DevBuf<uint32_t> d_wf_slot_job;
+    wrt::DevBuf<uint32_t> d_wf_keys, d_wf_sort_tmp, d_wf_sort_hist;  // ray reordering (wrt_kernels.h: WavefrontArgs::keys)
     wrt::DevBuf<unsigned long long> d_wf_counters;
     unsigned long long* h_wf_counters = nullptr;  // pinned
     cudaStream_t wf_streams[WRT_WF_MAX_PIPELINES] = {};  // [0] aliases `stream`

@@ -15,6 +15,26 @@
 
 namespace wrt {
 
+
+// 256-bit loads (sm_100: LDG.E.256).  The per-lane traversals read 64- and 128-byte records with every lane on its own
+// line, so the L1 pipeline spends one tag cycle per lane and INSTRUCTION whatever the width: half the instructions per
+// record is half that load.  Addresses must be 32-byte aligned (all records here are).
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+// streaming form (evict-first) for the path pool
+__device__ __forceinline__ void ldcs256(const void* p, double2& a, double2& b) {
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Device scene layout.  All records are 16-byte aligned and read with 128-bit loads.
 // ---------------------------------------------------------------------------------------------------------
@@ -123,6 +143,7 @@ struct DeviceScene {
     const Light* lights;
     const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
+    uint32_t prefetch;     // ordered traversal over four-wide records: 0 = no prefetch of deferred children, 1 = nearest deferred into L2, 2 = all deferred into L2, 3 = nearest deferred into L1
     uint32_t use_ordered;  // ordered traversal allowed (its worst-case stack use fits WRT_STACK_DEPTH)
     uint32_t use_wide;     // the ordered traversal walks the four-wide records (large trees) instead of the child-pair records
     uint32_t _pad1, _pad2;
@@ -492,7 +513,9 @@ __device__ __forceinline__ bool quad_plane_t(double num, double denom, double tm
 // evaluate the reference's expressions only inside that band, so every decision is the reference's.
 // `g` = the quad's record, `planar` = hit point - start.
 __device__ __forceinline__ bool quad_interior(const double2* __restrict__ g, d3 planar) {
-    const double2 c0 = __ldg(g + 4), c1 = __ldg(g + 5), c2 = __ldg(g + 6);
+    double2 c0, c1;
+    ldg256(g + 4, c0, c1);
+    const double2 c2 = __ldg(g + 6);
     const double a1 = dot(planar, mk(c0.x, c0.y, c1.x));
     const double b1 = dot(planar, mk(c1.y, c2.x, c2.y));
     // constant bands: if neither coordinate is flagged outside, |planar| is bounded by the quad's size and the rounding is
@@ -639,7 +662,8 @@ __device__ __forceinline__ void trav_init(const DeviceScene& S, Trav& T, d3 wo, 
 __device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
     {
         const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
-        const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+        float4 a0, a1, b0, b1;
+        ldg256(p, a0, a1); ldg256(p + 2, b0, b1);
         const float t_hi = __double2float_ru(T.best_t);
         float el, er = 0.0f;
         const bool hl = T.cull.entry(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, T.t_lo, t_hi, el);
@@ -661,13 +685,25 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, ui
     }
 }
 
+// A deferred child will be fetched when it is popped — unless a closer hit culls it first.  DRAM bandwidth is idle in the
+// ordered traversal (it waits on dependent fetches), so its line is requested now.
+__device__ __forceinline__ void trav_prefetch(const DeviceScene& S, uint32_t desc, uint32_t end, bool l1) {
+    const void* p;
+    if (desc & 0x80000000u) p = S.nodes4 + (desc & 0x7FFFFFFFu);
+    else if (end & WRT_LEAF_PRIM) p = (end & WRT_LEAF_QUAD) ? (const void*)(S.quads + (end & WRT_LEAF_INDEX)) : (const void*)(S.spheres + (end & WRT_LEAF_INDEX));
+    else p = S.ops + desc;
+    if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // One four-wide record: test the (up to) four children, go to the nearest one that is hit, defer the others so that the
 // nearer ones are popped first.  Order only steers the search (closest hit and tie rule do not depend on it), so the sort
 // runs on truncated keys: entry distance bits with the child index in the low two mantissa bits.
 __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
     const float4* p = reinterpret_cast<const float4*>(S.nodes4 + T.node);
-    const float4 lox = __ldg(p), loy = __ldg(p + 1), loz = __ldg(p + 2), hix = __ldg(p + 3), hiy = __ldg(p + 4), hiz = __ldg(p + 5);
-    const uint4 desc = __ldg(reinterpret_cast<const uint4*>(p) + 6), end = __ldg(reinterpret_cast<const uint4*>(p) + 7);
+    float4 lox, loy, loz, hix, hiy, hiz;
+    uint4 desc, end;
+    ldg256(p, lox, loy); ldg256(p + 2, loz, hix); ldg256(p + 4, hiy, hiz); ldg256(p + 6, desc, end);
     const float t_hi = __double2float_ru(T.best_t);
     float e0, e1, e2, e3;
     const bool h0 = T.cull.entry(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, T.t_lo, t_hi, e0) && desc.x != WRT_NONE;
@@ -685,9 +721,10 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, u
     auto pick_u = [](const uint4& v, uint32_t i) { return (i & 2u) ? ((i & 1u) ? v.w : v.z) : ((i & 1u) ? v.y : v.x); };
     auto pick_e = [&](uint32_t i) { return (i & 2u) ? ((i & 1u) ? e3 : e2) : ((i & 1u) ? e1 : e0); };
     // defer the far ones, farthest first (k3 >= k2 >= k1): the entry distance kept for the pop-time cull is the exact one
-    if (k3 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k3 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
-    if (k2 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k2 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
-    if (k1 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k1 & 3u; stack[T.sp++] = make_uint4(pick_u(desc, i), pick_u(end, i), T.xf, __float_as_uint(pick_e(i))); }
+    const uint32_t pf = S.prefetch;
+    if (k3 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k3 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf == 2u) trav_prefetch(S, dd, ee, false); }
+    if (k2 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k2 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf == 2u) trav_prefetch(S, dd, ee, false); }
+    if (k1 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k1 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf) trav_prefetch(S, dd, ee, pf == 3u); }
     if (k0 < miss) {
         const uint32_t i = k0 & 3u, go = pick_u(desc, i);
         if (go & 0x80000000u) { T.node = go & 0x7FFFFFFFu; }
@@ -724,7 +761,8 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T,
         T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
     } else if (op.x == OP_SPHERE) {
         const double2* g = reinterpret_cast<const double2*>(S.spheres + op.y);
-        double2 g0 = __ldg(g), g1 = __ldg(g + 1);
+        double2 g0, g1;
+        ldg256(g, g0, g1);
         d3 center = mk(g0.x, g0.y, g1.x);
         const double radius = g1.y;
         if (S.has_moving) {
@@ -748,13 +786,15 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T,
         T.pc = pc + 1;
     } else if (op.x == OP_QUAD) {
         const double2* g = reinterpret_cast<const double2*>(S.quads + op.y);
-        double2 n0 = __ldg(g), n1 = __ldg(g + 1);
+        double2 n0, n1;
+        ldg256(g, n0, n1);
         d3 n = mk(n0.x, n0.y, n1.x);
         double denom = dot(n, d);
         if (!(fabs(denom) < 1e-8)) {
             double t;
             if (quad_plane_t(n1.y - dot(n, o), denom, tmin, T.best_t, t)) {
-                double2 s0 = __ldg(g + 2), s1 = __ldg(g + 3);
+                double2 s0, s1;
+                ldg256(g + 2, s0, s1);
                 d3 p = o + d * t;
                 d3 planar = p - mk(s0.x, s0.y, s1.x);
                 if (quad_interior(g, planar)) {

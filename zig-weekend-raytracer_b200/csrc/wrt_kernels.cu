@@ -973,7 +973,7 @@ __device__ __forceinline__ PathState load_path(const PathState* p) {
     union { PathState s; double2 v[8]; } u;
     const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u.v[k] = __ldcs(q + k);
+    for (int k = 0; k < 8; k += 2) ldcs256(q + k, u.v[k], u.v[k + 1]);
     return u.s;
 }
 
@@ -987,6 +987,22 @@ __device__ __forceinline__ void wf_push(const WavefrontArgs& A, int q, bool pred
     if (lane == (uint32_t)leader) base = atomicAdd(&A.counters[q], (unsigned long long)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) wf_queue(A, q)[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+// the same, with the reordering key of the ray written beside the queue entry (extend queues only)
+__device__ __forceinline__ void wf_push_keyed(const WavefrontArgs& A, int q, bool pred, uint32_t slot, uint32_t key) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)leader) base = atomicAdd(&A.counters[q], (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        const size_t at = base + __popc(mask & ((1u << lane) - 1u));
+        wf_queue(A, q)[at] = slot;
+        A.keys[(size_t)(q - WQ_EXTEND0) * A.capacity + at] = key;
+    }
 }
 
 __device__ __forceinline__ void wf_slot_pixel(const RenderConstants& rc, const WavefrontArgs& A, uint32_t slot, uint32_t& chunk,
@@ -1208,7 +1224,9 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
     // without instances): it is re-read from the path pool there instead of living in 12 registers
     auto world_ray = [&](d3& wo, d3& wd, double& time) {
         const double2* p = reinterpret_cast<const double2*>(A.paths + slot);
-        const double2 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
+        double2 a, b;
+        ldcs256(p, a, b);
+        const double2 c = __ldcs(p + 2);
         wo = mk(a.x, a.y, b.x); wd = mk(b.y, c.x, c.y);
         time = S.has_moving ? A.paths[slot].time : 0.0;
     };
@@ -1304,7 +1322,7 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
     rng.k0 = (uint32_t)rc.seed; rng.k1 = (uint32_t)(rc.seed >> 32);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool valid = i < n;
-        uint32_t slot = 0;
+        uint32_t slot = 0, key = 0;
         bool extend = false, regen = false;
         if (valid) {
             slot = wf_queue(A, QUEUE)[i];
@@ -1344,11 +1362,57 @@ __global__ void __launch_bounds__(128) wf_shade_kernel(const __grid_constant__ L
                 }
                 out->depth_left = depth_left;
                 extend = true;
+                if (A.sort_buckets) {
+                    const uint32_t oct = (ray.d.x < 0.0 ? 1u : 0u) | (ray.d.y < 0.0 ? 2u : 0u) | (ray.d.z < 0.0 ? 4u : 0u);
+                    key = min(((ch.pc >> A.sort_shift) << 3) | oct, A.sort_buckets - 1u);
+                }
             }
         }
-        wf_push(A, q_extend, extend, slot);
+        if (A.sort_buckets) wf_push_keyed(A, q_extend, extend, slot, key);
+        else wf_push(A, q_extend, extend, slot);
         wf_push(A, q_regen, regen, slot);
     }
+}
+
+// ---- ray reordering: one counting-sort pass over the extend queue the shade kernels filled (WavefrontArgs::keys) ----------
+__global__ void __launch_bounds__(256) wf_sort_hist_kernel(WavefrontArgs A, uint32_t parity) {
+    const uint32_t n = (uint32_t)A.counters[WQ_EXTEND0 + parity];
+    const uint32_t* __restrict__ keys = A.keys + (size_t)parity * A.capacity;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&A.sort_hist[keys[i]], 1u);
+}
+__global__ void __launch_bounds__(1024) wf_sort_scan_kernel(WavefrontArgs A) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t nb = A.sort_buckets;
+    const uint32_t per = (nb + 1023u) / 1024u;
+    const uint32_t lo = min(threadIdx.x * per, nb), hi = min(lo + per, nb);
+    uint32_t sum = 0;
+    for (uint32_t b = lo; b < hi; ++b) sum += A.sort_hist[b];
+    uint32_t incl = sum;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (int m = 1; m < 32; m <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, m); if (lane >= (uint32_t)m) incl += v; }
+    if (lane == 31u) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t ws = warp_sums[lane];
+        for (int m = 1; m < 32; m <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, ws, m); if (lane >= (uint32_t)m) ws += v; }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    uint32_t run = incl - sum + (w ? warp_sums[w - 1] : 0u);
+    for (uint32_t b = lo; b < hi; ++b) { const uint32_t c = A.sort_hist[b]; A.sort_hist[b] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) wf_sort_scatter_kernel(WavefrontArgs A, uint32_t parity) {
+    const uint32_t n = (uint32_t)A.counters[WQ_EXTEND0 + parity];
+    const uint32_t* __restrict__ keys = A.keys + (size_t)parity * A.capacity;
+    const uint32_t* __restrict__ queue = wf_queue(A, WQ_EXTEND0 + (int)parity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        A.sort_tmp[atomicAdd(&A.sort_hist[keys[i]], 1u)] = queue[i];
+}
+__global__ void __launch_bounds__(256) wf_sort_copy_kernel(WavefrontArgs A, uint32_t parity) {
+    const uint32_t n = (uint32_t)A.counters[WQ_EXTEND0 + parity];
+    uint32_t* queue = wf_queue(A, WQ_EXTEND0 + (int)parity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) queue[i] = A.sort_tmp[i];
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < A.sort_buckets; b += gridDim.x * blockDim.x) A.sort_hist[b] = 0;
 }
 
 // reset the queues consumed by iteration `parity` so the next iteration can append to them
@@ -1468,6 +1532,12 @@ cudaError_t wf_extend_occupancy(int* blocks_per_sm) {
 }
 cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
                                 uint32_t grid, uint32_t persist_grid, cudaStream_t stream) {
+    if (A.sort_buckets) {  // reorder what the last iteration's shade kernels queued; wf_generate appends the camera rays behind it
+        wf_sort_hist_kernel<<<grid, 256, 0, stream>>>(A, parity);
+        wf_sort_scan_kernel<<<1, 1024, 0, stream>>>(A);
+        wf_sort_scatter_kernel<<<grid, 256, 0, stream>>>(A, parity);
+        wf_sort_copy_kernel<<<grid, 256, 0, stream>>>(A, parity);
+    }
     wf_generate_kernel<<<grid, 256, 0, stream>>>(lp, A, S, parity);
     const bool ordered = !packet && cull_mode != WRT_CULL_REFERENCE && S.use_ordered;
     if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)

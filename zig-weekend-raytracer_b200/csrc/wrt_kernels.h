@@ -72,6 +72,15 @@ struct WavefrontArgs {
     // milliseconds during which most of its lanes idle — the other pipeline's kernels fill the SMs.
     unsigned long long* shared;   // WS_* counters, common to all pipelines
     uint32_t job_base;            // the jobs this pipeline's slots start with: [job_base, job_base + capacity)
+    // Ray reordering (large trees): secondary rays are bucketed by where they START — the primitive they leave (its position in
+    // the program = a spatial order, the reference BVH's DFS order) and the octant of their direction — before the extend
+    // kernel draws them, so the lanes of a warp walk neighbouring parts of the tree.  One counting-sort pass per iteration:
+    // histogram, scan, scatter, copy back.  sort_buckets == 0: off.
+    uint32_t* keys;               // [2][capacity], parallel to the two extend queues
+    uint32_t* sort_tmp;           // [capacity]
+    uint32_t* sort_hist;          // [sort_buckets]
+    uint32_t sort_buckets;
+    uint32_t sort_shift;          // key = ((hit op >> sort_shift) << 3) | direction octant
 };
 enum { WS_JOB_CURSOR = 0, WS_JOBS_DONE = 1, WS_RAYS = 2, WS_PATHS = 3, WS_STEPS = 4, WS_COUNT = 8 };
 
