@@ -1,0 +1,13 @@
+#!/bin/bash
+# lean traversal state in the persistent extend kernel: 6 / 7 / 8 resident blocks per SM (80 / 72 / 64 registers)
+set -u
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -m gpu -x -q > gpurun_out/r02_run20_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r02_run20_pytest.log
+run() { python bench.py "${@:2}" --no-cpu-baseline --no-all-workloads 2>gpurun_out/r02_run20_$1.err | python -c "
+import sys,json
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{\"metric')][-1]); print('$1', round(d['value'],1), 'Mrays/s', round(d['ms_per_step'],1), 'ms', d['mean_radiance'], d['gpu_launches'], 'e2e', round(d['e2e']['value'],1))"; }
+C5="--workload C5 --spp 64 --steps 1 --warmup 1 --warmup-spp 2 --fused-e2e"
+WRT_WF_BLOCKS=6 run b6 $C5
+WRT_WF_BLOCKS=7 run b7 $C5
+WRT_WF_BLOCKS=8 run b8 $C5
+WRT_WF_BLOCKS=8 WRT_WF_POOL=64 run b8_pool64 $C5

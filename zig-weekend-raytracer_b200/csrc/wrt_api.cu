@@ -55,7 +55,7 @@ uint32_t log2u(uint32_t v) {
 }  // namespace
 
 #ifndef WRT_WF_POOL_SLOTS
-#define WRT_WF_POOL_SLOTS (32ull << 20)  // path slots of the wavefront pool (128 B of state + 32 B of queue / job space each)
+#define WRT_WF_POOL_SLOTS (64ull << 20)  // path slots of the wavefront pool (128 B of state + 32 B of queue / job space each)
 #endif
 #ifndef WRT_WF_PIPELINES
 #define WRT_WF_PIPELINES 4u  // independent pipelines the pool is cut into (wrt_kernels.h: WavefrontArgs::shared)

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/wrt.h"
 #include "wrt_kernels.h"
@@ -634,20 +635,43 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 #define WRT_WIDE_TREE_MIN_RECORDS 16384u
 #endif
 // The traversal state.
-struct Trav {
+// LEAN: the binary64 ray in the current transform context is NOT kept in the state (12 registers that are dead weight while
+// a lane walks box records, which only need the culler's binary32 copy): the leaf ops re-form it from the world-space ray the
+// caller can re-read (the persistent extend kernel: 48 bytes of its path record).  Buys the occupancy step of that kernel.
+struct TravRay { d3 o, d; };  // ray in the current transform context
+struct TravNoRay {};
+template <bool LEAN>
+struct TravT : std::conditional<LEAN, TravNoRay, TravRay>::type {
+    static constexpr bool lean = LEAN;
     double best_t;
-    d3 o, d;  // ray in the current transform context
     uint32_t first_pc, first_xf, lastq_pc, lastq_xf;
     uint32_t xf, pc, end, node;
     int sp;
     float t_lo;
     Culler<WRT_CULL_TIGHT> cull;
 };
+using Trav = TravT<false>;
+using TravLean = TravT<true>;
 
-__device__ __forceinline__ void trav_init(const DeviceScene& S, Trav& T, d3 wo, d3 wd, double time, double tmin, double tmax) {
+// the ray in the state's current transform context
+template <class TR, typename WORLD>
+__device__ __forceinline__ void trav_local_ray(const DeviceScene& S, const TR& T, WORLD&& world, d3& o, d3& d) {
+    if constexpr (TR::lean) {
+        d3 wo, wd;
+        double time;
+        world(wo, wd, time);
+        if (T.xf == WRT_NONE) { o = wo; d = wd; }
+        else ray_in_xform(S, T.xf, wo, wd, o, d);
+    } else {
+        o = T.o; d = T.d;
+    }
+}
+
+template <class TR>
+__device__ __forceinline__ void trav_init(const DeviceScene& S, TR& T, d3 wo, d3 wd, double time, double tmin, double tmax) {
     (void)time;
     T.best_t = tmax;
-    T.o = wo; T.d = wd;
+    if constexpr (!TR::lean) { T.o = wo; T.d = wd; }
     T.first_pc = WRT_NONE; T.first_xf = WRT_NONE; T.lastq_pc = WRT_NONE; T.lastq_xf = WRT_NONE;
     T.xf = WRT_NONE;
     T.cull.set_ray(wo, wd);
@@ -659,7 +683,8 @@ __device__ __forceinline__ void trav_init(const DeviceScene& S, Trav& T, d3 wo, 
 
 // One child-pair record: test both children, go to the nearer one that is hit, defer the other.  Leaves T.node set (next
 // record), or a leaf op range in (T.pc, T.end), or an empty range (nothing hit: the caller pops).
-__device__ __forceinline__ void trav_node_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+template <class TR>
+__device__ __forceinline__ void trav_node_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
     {
         const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
         float4 a0, a1, b0, b1;
@@ -699,7 +724,8 @@ __device__ __forceinline__ void trav_prefetch(const DeviceScene& S, uint32_t des
 // One four-wide record: test the (up to) four children, go to the nearest one that is hit, defer the others so that the
 // nearer ones are popped first.  Order only steers the search (closest hit and tie rule do not depend on it), so the sort
 // runs on truncated keys: entry distance bits with the child index in the low two mantissa bits.
-__device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+template <class TR>
+__device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
     const float4* p = reinterpret_cast<const float4*>(S.nodes4 + T.node);
     float4 lox, loy, loz, hix, hiy, hiz;
     uint4 desc, end;
@@ -736,15 +762,15 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, Trav& T, u
 
 // WIDE: 0 = child-pair records, 1 = four-wide records (the hot kernels are instantiated for the form the scene uses: a run-time
 // switch inside the per-lane megakernel's record loop cost the 484-sphere scene 7 %), 2 = ask the scene (gates, diagnostics)
-template <int WIDE = 2>
-__device__ __forceinline__ void trav_record_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack) {
+template <int WIDE = 2, class TR>
+__device__ __forceinline__ void trav_record_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
     if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
     else trav_node_step(S, T, stack);
 }
 
 // One op of the current leaf range (T.pc < T.end).
-template <typename WORLD>
-__device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
+template <class TR, typename WORLD>
+__device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
     const uint32_t pc = T.pc;
     uint4 op;
     if (T.end & WRT_LEAF_PRIM) {  // single-primitive leaf of a four-wide record: kind and record index travel in `end`, so the
@@ -753,7 +779,8 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T,
     } else {
         op = __ldg(S.ops + pc);
     }
-    const d3 o = T.o, d = T.d;
+    d3 o, d;
+    trav_local_ray(S, T, world, o, d);
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
         if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
         T.node = S.use_wide ? __ldg(S.root4 + op.y) : op.y;
@@ -808,14 +835,16 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T,
         }
         T.pc = pc + 1;
     } else if (op.x == OP_PUSH_TRANSLATE || op.x == OP_PUSH_ROTATE_Y) {
-        apply_xform(S.xforms[op.y], T.o, T.d);
+        apply_xform(S.xforms[op.y], o, d);
+        if constexpr (!TR::lean) { T.o = o; T.d = d; }
         T.xf = op.y;
-        T.cull.set_ray(T.o, T.d);
+        T.cull.set_ray(o, d);
         T.pc = pc + 1;
     } else if (op.x == OP_POP) {
         T.xf = op.y;
-        { d3 wo, wd; double time; world(wo, wd, time); ray_in_xform(S, T.xf, wo, wd, T.o, T.d); }
-        T.cull.set_ray(T.o, T.d);
+        { d3 wo, wd; double time; world(wo, wd, time); ray_in_xform(S, T.xf, wo, wd, o, d); }
+        if constexpr (!TR::lean) { T.o = o; T.d = d; }
+        T.cull.set_ray(o, d);
         T.pc = pc + 1;
     } else {
         T.pc = T.end;  // OP_END
@@ -824,12 +853,20 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, Trav& T,
 
 // Range exhausted: resume the nearest deferred subtree that can still hold a closer hit.  Returns true when the stack is
 // empty (the traversal is complete).
-template <typename WORLD>
-__device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world) {
+template <class TR, typename WORLD>
+__device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world) {
     while (T.sp > 0) {
         const uint4 e = stack[--T.sp];
         if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
-        if (e.z != T.xf) { T.xf = e.z; d3 wo, wd; double time; world(wo, wd, time); ray_in_xform(S, T.xf, wo, wd, T.o, T.d); T.cull.set_ray(T.o, T.d); }
+        if (e.z != T.xf) {
+            T.xf = e.z;
+            d3 wo, wd, o, d;
+            double time;
+            world(wo, wd, time);
+            ray_in_xform(S, T.xf, wo, wd, o, d);
+            if constexpr (!TR::lean) { T.o = o; T.d = d; }
+            T.cull.set_ray(o, d);
+        }
         if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
         else { T.node = WRT_NONE; T.pc = e.x; T.end = e.y; }
         return false;
@@ -839,8 +876,8 @@ __device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, Trav& T, uin
 
 // One op of the current leaf range (if any is left), then — when that exhausted the range — the pop, so a single-primitive
 // leaf costs one step and leaves the lane on its next record.  Returns true when the traversal is complete.
-template <typename WORLD>
-__device__ __forceinline__ bool trav_leaf_step_lazy(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
+template <class TR, typename WORLD>
+__device__ __forceinline__ bool trav_leaf_step_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
     if (T.pc < T.end) trav_leaf_op_lazy(S, T, stack, world, tmin, tmax);
     if (T.node == WRT_NONE && T.pc >= T.end) return trav_pop_lazy(S, T, stack, world);
     return false;
@@ -851,7 +888,8 @@ __device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, ui
     return trav_leaf_step_lazy(S, T, stack, [&](d3& o_, d3& d_, double& t_) { o_ = wo; d_ = wd; t_ = time; }, tmin, tmax);
 }
 
-__device__ __forceinline__ ClosestHit trav_result(const Trav& T) {
+template <class TR>
+__device__ __forceinline__ ClosestHit trav_result(const TR& T) {
     ClosestHit best;
     best.t = T.best_t;
     const bool quad_wins = (T.lastq_pc != WRT_NONE) && (T.first_pc != WRT_NONE) && (T.lastq_pc > T.first_pc);

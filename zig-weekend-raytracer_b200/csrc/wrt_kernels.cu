@@ -14,6 +14,8 @@
 
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "wrt_device.cuh"
 #include "wrt_kernels.h"
 
@@ -1158,6 +1160,9 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
 #ifndef WRT_WF_EXTEND_MIN_BLOCKS
 #define WRT_WF_EXTEND_MIN_BLOCKS 6  // <= 85 registers: 24 warps per SM (the kernel is bound by memory latency, not by issue)
 #endif
+#ifndef WRT_WF_EXTEND_DEFAULT_BLOCKS
+#define WRT_WF_EXTEND_DEFAULT_BLOCKS 8  // 64 registers, 32 warps per SM (measured 6 / 7 / 8 blocks: 698 / 731 / 732 Mrays/s on C5); what the wide (four-wide records) instantiation runs with unless WRT_WF_BLOCKS says otherwise
+#endif
 #ifndef WRT_WF_CURSOR_CHUNK
 #define WRT_WF_CURSOR_CHUNK 256u    // most queue entries a warp draws per atomic
 #endif
@@ -1198,8 +1203,8 @@ __device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& 
     if (lane + 32u < count) wf_queue(A, queue)[base + 32u + lane] = st.slot[row][lane + 32u];
 }
 
-template <int WIDE>
-__global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
+template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     __shared__ WfStage stage[4];  // one per warp of the block
     const RenderConstants& rc = LP.rc;
     const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
@@ -1214,7 +1219,7 @@ __global__ void __launch_bounds__(128, WRT_WF_EXTEND_MIN_BLOCKS) wf_extend_order
     // chunk: a few draws per warp on a full queue, but never so large that a short queue lands on a handful of warps
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t chunk = max(32u, min((uint32_t)WRT_WF_CURSOR_CHUNK, (n / (2u * n_warps)) & ~31u));
-    Trav T;
+    TravLean T;  // the local ray is re-formed from the path record where a leaf op needs it
     uint4 stack[WRT_STACK_DEPTH];
     uint32_t slot = 0;
     bool has = false, drained = false;
@@ -1527,7 +1532,19 @@ cudaError_t wf_launch_init(const LaunchParams& lp, const WavefrontArgs& A, uint3
     return cudaGetLastError();
 }
 // One wavefront iteration: generate -> extend -> shade (surface, metal, other) -> reset of the consumed queues.
+// resident blocks per SM the wide extend kernel is compiled for: WRT_WF_BLOCKS = 6 (80 registers), 7 (72) or 8 (64)
+static int wf_extend_min_blocks() {
+    static const int v = [] {
+        const char* env = std::getenv("WRT_WF_BLOCKS");
+        const int b = env ? std::atoi(env) : WRT_WF_EXTEND_DEFAULT_BLOCKS;
+        return (b == 6 || b == 7 || b == 8) ? b : WRT_WF_EXTEND_DEFAULT_BLOCKS;
+    }();
+    return v;
+}
 cudaError_t wf_extend_occupancy(int* blocks_per_sm) {
+    const int b = wf_extend_min_blocks();
+    if (b == 8) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel<1, 8>, 128, 0);
+    if (b == 7) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel<1, 7>, 128, 0);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wf_extend_ordered_kernel<1>, 128, 0);
 }
 cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, const DeviceScene& S, uint32_t cull_mode, bool packet, uint32_t parity,
@@ -1541,7 +1558,12 @@ cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, 
     wf_generate_kernel<<<grid, 256, 0, stream>>>(lp, A, S, parity);
     const bool ordered = !packet && cull_mode != WRT_CULL_REFERENCE && S.use_ordered;
     if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)
-        if (S.use_wide) wf_extend_ordered_kernel<1><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+        if (S.use_wide) {
+            const int b = wf_extend_min_blocks();
+            if (b == 8) wf_extend_ordered_kernel<1, 8><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            else if (b == 7) wf_extend_ordered_kernel<1, 7><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            else wf_extend_ordered_kernel<1><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+        }
         else wf_extend_ordered_kernel<0><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
     } else {
         dispatch(cull_mode, packet, [&](auto c, auto t) {
