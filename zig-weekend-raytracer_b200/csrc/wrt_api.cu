@@ -312,8 +312,6 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     // ordered traversal only when its exact worst-case stack use fits (ordered_stack_depth walks the rebuilt trees)
     ds.use_ordered = (cs.stack_depth <= WRT_STACK_DEPTH) ? 1u : 0u;
     ds.use_wide = cs.use_wide ? 1u : 0u;
-    ds.prefetch = 0u;
-    if (const char* env = std::getenv("WRT_TRAV_PREFETCH")) ds.prefetch = (uint32_t)std::atoi(env);
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
     // Large trees: ask L2 to keep the four-wide records (the dependent fetches of every traversal step) in preference to the

@@ -144,7 +144,6 @@ struct DeviceScene {
     const Light* lights;
     const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
-    uint32_t prefetch;     // ordered traversal over four-wide records: 0 = no prefetch of deferred children, 1 = nearest deferred into L2, 2 = all deferred into L2, 3 = nearest deferred into L1
     uint32_t use_ordered;  // ordered traversal allowed (its worst-case stack use fits WRT_STACK_DEPTH)
     uint32_t use_wide;     // the ordered traversal walks the four-wide records (large trees) instead of the child-pair records
     uint32_t _pad1, _pad2;
@@ -635,6 +634,24 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 #define WRT_WIDE_TREE_MIN_RECORDS 16384u
 #endif
 // The traversal state.
+// The per-lane traversal stack: entries {desc | first op, end op, xform, entry distance bits}.  TravLocalStack lives in local
+// memory (lane-interleaved: an entry of a lane whose neighbours stand at other depths costs four 32-byte sectors per access,
+// and the stacks of the resident warps fill most of L1).  TravHybridStack keeps the bottom D entries — where nearly all
+// pushes and pops happen — in shared memory, one column per thread ([entry][thread]: the bank depends on the thread only, so
+// lanes at different depths do not conflict), the rest in local memory.
+struct TravLocalStack {
+    uint4 e[WRT_STACK_DEPTH];
+    __device__ __forceinline__ void put(int i, uint4 v) { e[i] = v; }
+    __device__ __forceinline__ uint4 get(int i) const { return e[i]; }
+};
+template <int D, int THREADS>
+struct TravHybridStack {
+    uint4 e[WRT_STACK_DEPTH - D];
+    uint4* column;  // shared memory: this thread's entry 0; entry i is column[i * THREADS]
+    __device__ __forceinline__ void put(int i, uint4 v) { if (i < D) column[i * THREADS] = v; else e[i - D] = v; }
+    __device__ __forceinline__ uint4 get(int i) const { return (i < D) ? column[i * THREADS] : e[i - D]; }
+};
+
 // LEAN: the binary64 ray in the current transform context is NOT kept in the state (12 registers that are dead weight while
 // a lane walks box records, which only need the culler's binary32 copy): the leaf ops re-form it from the world-space ray the
 // caller can re-read (the persistent extend kernel: 48 bytes of its path record).  Buys the occupancy step of that kernel.
@@ -683,8 +700,8 @@ __device__ __forceinline__ void trav_init(const DeviceScene& S, TR& T, d3 wo, d3
 
 // One child-pair record: test both children, go to the nearer one that is hit, defer the other.  Leaves T.node set (next
 // record), or a leaf op range in (T.pc, T.end), or an empty range (nothing hit: the caller pops).
-template <class TR>
-__device__ __forceinline__ void trav_node_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
+template <class TR, class STK>
+__device__ __forceinline__ void trav_node_step(const DeviceScene& S, TR& T, STK& stack) {
     {
         const float4* p = reinterpret_cast<const float4*>(S.nodes2 + T.node);
         float4 a0, a1, b0, b1;
@@ -699,7 +716,7 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, TR& T, uint
         const bool both = hl && hr;
         const bool go_left = both ? (el <= er) : hl;
         if (both && T.sp < WRT_STACK_DEPTH)
-            stack[T.sp++] = make_uint4(go_left ? r_desc : l_desc, go_left ? r_end : l_end, T.xf, __float_as_uint(go_left ? er : el));
+            stack.put(T.sp++, make_uint4(go_left ? r_desc : l_desc, go_left ? r_end : l_end, T.xf, __float_as_uint(go_left ? er : el)));
         if (hl || hr) {
             const uint32_t go_desc = go_left ? l_desc : r_desc;
             if (go_desc & 0x80000000u) { T.node = go_desc & 0x7FFFFFFFu; }
@@ -710,22 +727,11 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene& S, TR& T, uint
     }
 }
 
-// A deferred child will be fetched when it is popped — unless a closer hit culls it first.  DRAM bandwidth is idle in the
-// ordered traversal (it waits on dependent fetches), so its line is requested now.
-__device__ __forceinline__ void trav_prefetch(const DeviceScene& S, uint32_t desc, uint32_t end, bool l1) {
-    const void* p;
-    if (desc & 0x80000000u) p = S.nodes4 + (desc & 0x7FFFFFFFu);
-    else if (end & WRT_LEAF_PRIM) p = (end & WRT_LEAF_QUAD) ? (const void*)(S.quads + (end & WRT_LEAF_INDEX)) : (const void*)(S.spheres + (end & WRT_LEAF_INDEX));
-    else p = S.ops + desc;
-    if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 // One four-wide record: test the (up to) four children, go to the nearest one that is hit, defer the others so that the
 // nearer ones are popped first.  Order only steers the search (closest hit and tie rule do not depend on it), so the sort
 // runs on truncated keys: entry distance bits with the child index in the low two mantissa bits.
-template <class TR>
-__device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
+template <class TR, class STK>
+__device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, STK& stack) {
     const float4* p = reinterpret_cast<const float4*>(S.nodes4 + T.node);
     float4 lox, loy, loz, hix, hiy, hiz;
     uint4 desc, end;
@@ -747,10 +753,9 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, uin
     auto pick_u = [](const uint4& v, uint32_t i) { return (i & 2u) ? ((i & 1u) ? v.w : v.z) : ((i & 1u) ? v.y : v.x); };
     auto pick_e = [&](uint32_t i) { return (i & 2u) ? ((i & 1u) ? e3 : e2) : ((i & 1u) ? e1 : e0); };
     // defer the far ones, farthest first (k3 >= k2 >= k1): the entry distance kept for the pop-time cull is the exact one
-    const uint32_t pf = S.prefetch;
-    if (k3 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k3 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf == 2u) trav_prefetch(S, dd, ee, false); }
-    if (k2 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k2 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf == 2u) trav_prefetch(S, dd, ee, false); }
-    if (k1 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k1 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack[T.sp++] = make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i))); if (pf) trav_prefetch(S, dd, ee, pf == 3u); }
+    if (k3 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k3 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack.put(T.sp++, make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i)))); }
+    if (k2 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k2 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack.put(T.sp++, make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i)))); }
+    if (k1 < miss && T.sp < WRT_STACK_DEPTH) { const uint32_t i = k1 & 3u; const uint32_t dd = pick_u(desc, i), ee = pick_u(end, i); stack.put(T.sp++, make_uint4(dd, ee, T.xf, __float_as_uint(pick_e(i)))); }
     if (k0 < miss) {
         const uint32_t i = k0 & 3u, go = pick_u(desc, i);
         if (go & 0x80000000u) { T.node = go & 0x7FFFFFFFu; }
@@ -762,15 +767,15 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, uin
 
 // WIDE: 0 = child-pair records, 1 = four-wide records (the hot kernels are instantiated for the form the scene uses: a run-time
 // switch inside the per-lane megakernel's record loop cost the 484-sphere scene 7 %), 2 = ask the scene (gates, diagnostics)
-template <int WIDE = 2, class TR>
-__device__ __forceinline__ void trav_record_step(const DeviceScene& S, TR& T, uint4* __restrict__ stack) {
+template <int WIDE = 2, class TR, class STK>
+__device__ __forceinline__ void trav_record_step(const DeviceScene& S, TR& T, STK& stack) {
     if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
     else trav_node_step(S, T, stack);
 }
 
 // One op of the current leaf range (T.pc < T.end).
-template <class TR, typename WORLD>
-__device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
+template <class TR, class STK, typename WORLD>
+__device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, STK& stack, WORLD&& world, double tmin, double tmax) {
     const uint32_t pc = T.pc;
     uint4 op;
     if (T.end & WRT_LEAF_PRIM) {  // single-primitive leaf of a four-wide record: kind and record index travel in `end`, so the
@@ -782,7 +787,7 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, u
     d3 o, d;
     trav_local_ray(S, T, world, o, d);
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
-        if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack[T.sp++] = make_uint4(op.z, T.end, T.xf, 0u);
+        if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint4(op.z, T.end, T.xf, 0u));
         T.node = S.use_wide ? __ldg(S.root4 + op.y) : op.y;
     } else if (op.x == OP_NODE_TIGHT_ONLY) {
         T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
@@ -853,10 +858,10 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, u
 
 // Range exhausted: resume the nearest deferred subtree that can still hold a closer hit.  Returns true when the stack is
 // empty (the traversal is complete).
-template <class TR, typename WORLD>
-__device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world) {
+template <class TR, class STK, typename WORLD>
+__device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, STK& stack, WORLD&& world) {
     while (T.sp > 0) {
-        const uint4 e = stack[--T.sp];
+        const uint4 e = stack.get(--T.sp);
         if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
         if (e.z != T.xf) {
             T.xf = e.z;
@@ -876,14 +881,15 @@ __device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, uint4
 
 // One op of the current leaf range (if any is left), then — when that exhausted the range — the pop, so a single-primitive
 // leaf costs one step and leaves the lane on its next record.  Returns true when the traversal is complete.
-template <class TR, typename WORLD>
-__device__ __forceinline__ bool trav_leaf_step_lazy(const DeviceScene& S, TR& T, uint4* __restrict__ stack, WORLD&& world, double tmin, double tmax) {
+template <class TR, class STK, typename WORLD>
+__device__ __forceinline__ bool trav_leaf_step_lazy(const DeviceScene& S, TR& T, STK& stack, WORLD&& world, double tmin, double tmax) {
     if (T.pc < T.end) trav_leaf_op_lazy(S, T, stack, world, tmin, tmax);
     if (T.node == WRT_NONE && T.pc >= T.end) return trav_pop_lazy(S, T, stack, world);
     return false;
 }
 // the same with the world-space ray at hand (megakernels, gates)
-__device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, uint4* __restrict__ stack, const d3& wo, const d3& wd, double time,
+template <class STK>
+__device__ __forceinline__ bool trav_leaf_step(const DeviceScene& S, Trav& T, STK& stack, const d3& wo, const d3& wd, double time,
                                                double tmin, double tmax) {
     return trav_leaf_step_lazy(S, T, stack, [&](d3& o_, d3& d_, double& t_) { o_ = wo; d_ = wd; t_ = time; }, tmin, tmax);
 }
@@ -901,7 +907,7 @@ __device__ __forceinline__ ClosestHit trav_result(const TR& T) {
 template <int WIDE = 2>
 __device__ inline ClosestHit closest_hit_ordered(const DeviceScene& S, d3 wo, d3 wd, double time, double tmin, double tmax) {
     Trav T;
-    uint4 stack[WRT_STACK_DEPTH];  // {desc | first op, end op, xform, entry distance bits}
+    TravLocalStack stack;
     trav_init(S, T, wo, wd, time, tmin, tmax);
     // "while-while": every lane first descends through box records until it stands on a leaf range (cheap binary32 steps),
     // then the lanes of the warp run their binary64 primitive tests together

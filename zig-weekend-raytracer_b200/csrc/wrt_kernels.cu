@@ -1169,7 +1169,13 @@ __global__ void __launch_bounds__(128) wf_extend_kernel(const __grid_constant__ 
 // Output queues are fed through per-warp staging rows in shared memory: a retiring lane drops its slot there and the warp
 // appends a full row of 32 with ONE atomic (the plain wf_push costs one atomic per warp per retire event, and with lanes
 // retiring one or two at a time four counters were taking 10^8 atomics a second).
-#define WRT_WF_STAGE 64  // entries per (warp, queue) row: < 32 before a retire event adds <= 32
+// A row is appended when it holds WRT_WF_STAGE_FLUSH entries; with 16 the four rows of a warp take 768 bytes, a block 3 KB (+ 1 KB
+// the system reserves), and eight resident blocks fit the 32 KB shared-memory configuration — the next one (64 KB) would take 32 KB
+// of L1 away from the tree records.
+#ifndef WRT_WF_STAGE_FLUSH
+#define WRT_WF_STAGE_FLUSH 16u
+#endif
+#define WRT_WF_STAGE (WRT_WF_STAGE_FLUSH + 32u)  // entries per (warp, queue) row: < FLUSH before a retire event adds <= 32
 struct WfStage {
     uint32_t slot[4][WRT_WF_STAGE];
 };
@@ -1179,15 +1185,16 @@ __device__ __forceinline__ void wf_stage_push(const WavefrontArgs& A, WfStage& s
     if (pred) st.slot[row][count + __popc(mask & ((1u << lane) - 1u))] = slot;
     count += __popc(mask);
     __syncwarp();
-    if (count >= 32u) {  // append the oldest 32, keep the rest
+    if (count >= WRT_WF_STAGE_FLUSH) {  // append the oldest min(count, 32), keep the rest
+        const uint32_t out = min(count, 32u);
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&A.counters[queue], 32ull);
+        if (lane == 0) base = atomicAdd(&A.counters[queue], (unsigned long long)out);
         base = __shfl_sync(0xffffffffu, base, 0);
-        wf_queue(A, queue)[base + lane] = st.slot[row][lane];
+        if (lane < out) wf_queue(A, queue)[base + lane] = st.slot[row][lane];
         __syncwarp();
-        const uint32_t rest = count - 32u;
+        const uint32_t rest = count - out;
         uint32_t moved = 0;
-        if (lane < rest) moved = st.slot[row][32u + lane];
+        if (lane < rest) moved = st.slot[row][out + lane];
         __syncwarp();
         if (lane < rest) st.slot[row][lane] = moved;
         count = rest;
@@ -1203,9 +1210,15 @@ __device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& 
     if (lane + 32u < count) wf_queue(A, queue)[base + 32u + lane] = st.slot[row][lane + 32u];
 }
 
-template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS>
+template <int N> struct WfStackColumns { __device__ __forceinline__ static uint4* get() { __shared__ uint4 a[N * 128]; return a; } };
+template <> struct WfStackColumns<0> { __device__ __forceinline__ static uint4* get() { return nullptr; } };
+template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS, int SMSTACK = 0>
 __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     __shared__ WfStage stage[4];  // one per warp of the block
+    // SMSTACK > 0 keeps the bottom entries of every thread's stack in shared memory.  Measured on C5 (8 blocks / SM): 0 / 4 / 6 / 8
+    // entries = 755 / 686 / 676 / 661 Mrays/s — the shared memory comes out of L1, and the records' L1 hits are worth more than
+    // the local-memory sectors saved.  Not instantiated.
+    uint4* const stack_columns = WfStackColumns<SMSTACK>::get();
     const RenderConstants& rc = LP.rc;
     const int q_in = WQ_EXTEND0 + (int)parity, q_regen = WQ_REGEN0 + (int)(parity ^ 1u);
     const uint32_t n = (uint32_t)A.counters[q_in];
@@ -1220,7 +1233,8 @@ __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __gr
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t chunk = max(32u, min((uint32_t)WRT_WF_CURSOR_CHUNK, (n / (2u * n_warps)) & ~31u));
     TravLean T;  // the local ray is re-formed from the path record where a leaf op needs it
-    uint4 stack[WRT_STACK_DEPTH];
+    typename std::conditional<SMSTACK != 0, TravHybridStack<(SMSTACK ? SMSTACK : 1), 128>, TravLocalStack>::type stack;
+    if constexpr (SMSTACK != 0) stack.column = stack_columns + threadIdx.x;
     uint32_t slot = 0;
     bool has = false, drained = false;
     T.node = WRT_NONE; T.pc = 0; T.end = 0; T.sp = 0;

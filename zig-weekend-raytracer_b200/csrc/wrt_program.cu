@@ -691,33 +691,6 @@ struct HostTreeBuilder {
                 level.swap(next_level);
             }
         }
-        if (const char* env = std::getenv("WRT_NODE4_ORDER")) {  // experiment: depth-first numbering of the same records (host build only)
-            if (env[0] == 'd') {
-                const uint32_t n4 = (uint32_t)out.nodes4.size();
-                std::vector<uint32_t> new_index(n4, WRT_NONE), stack;
-                uint32_t next = 0;
-                for (const TreeInput& r : out.tree_inputs) {
-                    stack.assign(1, out.root4[r.record]);
-                    while (!stack.empty()) {
-                        const uint32_t rec = stack.back();
-                        stack.pop_back();
-                        new_index[rec] = next++;
-                        const Node4& n = out.nodes4[rec];
-                        for (int i = 3; i >= 0; --i)
-                            if (n.desc[i] != WRT_NONE && (n.desc[i] & 0x80000000u)) stack.push_back(n.desc[i] & 0x7FFFFFFFu);
-                    }
-                }
-                std::vector<Node4> renum(n4);
-                for (uint32_t rec = 0; rec < n4; ++rec) {
-                    Node4 n = out.nodes4[rec];
-                    for (int i = 0; i < 4; ++i)
-                        if (n.desc[i] != WRT_NONE && (n.desc[i] & 0x80000000u)) n.desc[i] = 0x80000000u | new_index[n.desc[i] & 0x7FFFFFFFu];
-                    renum[new_index[rec]] = n;
-                }
-                out.nodes4.swap(renum);
-                for (const TreeInput& r : out.tree_inputs) out.root4[r.record] = new_index[out.root4[r.record]];
-            }
-        }
     }
 };
 
