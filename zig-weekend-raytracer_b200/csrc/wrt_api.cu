@@ -196,7 +196,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     wrt::comm_release(ctx);
     ctx->d_shard.release(); ctx->d_staging.release();
     ctx->free_images();
-    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_nodes4.release(); ctx->d_root4.release(); ctx->d_spheres.release();
+    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_nodes4.release(); ctx->d_root4.release(); ctx->d_sphere_pc.release(); ctx->d_quad_pc.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
@@ -290,6 +290,8 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     CU(ctx->d_nodes2.upload(cs.nodes2, ctx->stream));
     CU(ctx->d_nodes4.upload(cs.nodes4, ctx->stream));
     CU(ctx->d_root4.upload(cs.root4, ctx->stream));
+    CU(ctx->d_sphere_pc.upload(cs.sphere_pc, ctx->stream));
+    CU(ctx->d_quad_pc.upload(cs.quad_pc, ctx->stream));
     CU(ctx->d_spheres.upload(cs.spheres, ctx->stream));
     CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
     CU(ctx->d_quads.upload(cs.quads, ctx->stream));
@@ -312,6 +314,11 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     // ordered traversal only when its exact worst-case stack use fits (ordered_stack_depth walks the rebuilt trees)
     ds.use_ordered = (cs.stack_depth <= WRT_STACK_DEPTH) ? 1u : 0u;
     ds.use_wide = cs.use_wide ? 1u : 0u;
+    ds.sphere_pc = ctx->d_sphere_pc.p; ds.quad_pc = ctx->d_quad_pc.p;
+    {
+        const char* env = std::getenv("WRT_COMPACT_STACK");  // A/B switch: 0 keeps the 16-byte entries
+        ds.compact_ok = (cs.compact_ok && !(env && env[0] == '0')) ? 1u : 0u;
+    }
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
     // Large trees: ask L2 to keep the four-wide records (the dependent fetches of every traversal step) in preference to the

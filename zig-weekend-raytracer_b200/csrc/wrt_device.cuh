@@ -144,6 +144,9 @@ struct DeviceScene {
     const Light* lights;
     const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
+    const uint32_t* sphere_pc;  // per sphere / quad record: the op that tests it (compact stack entries, see TravCompactStack)
+    const uint32_t* quad_pc;
+    uint32_t compact_ok;   // one tree of single-primitive leaves, no transforms, every primitive tested by exactly one op
     uint32_t use_ordered;  // ordered traversal allowed (its worst-case stack use fits WRT_STACK_DEPTH)
     uint32_t use_wide;     // the ordered traversal walks the four-wide records (large trees) instead of the child-pair records
     uint32_t _pad1, _pad2;
@@ -640,12 +643,29 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 // pushes and pops happen — in shared memory, one column per thread ([entry][thread]: the bank depends on the thread only, so
 // lanes at different depths do not conflict), the rest in local memory.
 struct TravLocalStack {
+    static constexpr bool compact = false;
     uint4 e[WRT_STACK_DEPTH];
     __device__ __forceinline__ void put(int i, uint4 v) { e[i] = v; }
     __device__ __forceinline__ uint4 get(int i) const { return e[i]; }
 };
+// COMPACT entries, 8 bytes: {child word, sort key}.  For scenes that are ONE tree of single-primitive leaves without
+// transforms (DeviceScene::compact_ok — the 2^20-primitive scene): a deferred child is its record (bit 31 set) or its
+// primitive (kind bit 30 + record index), the key is the entry distance with the low two mantissa bits cleared — never
+// above the exact distance, so the pop-time cull stays conservative.  There is no transform context to restore and no
+// range to resume.  The program position of a primitive (the tie rule compares positions) is not carried: it is looked
+// up in sphere_pc / quad_pc when the primitive is actually hit.  Half the local-memory sectors per push / pop, half the
+// L1 the lane stacks occupy (L1 capacity is what the tree records want), and the sort moves (key, word) pairs, so no
+// child field is picked by index afterwards.
+#define WRT_PC_UNKNOWN 0x7FFFFFF0u
+struct TravCompactStack {
+    static constexpr bool compact = true;
+    uint2 e[WRT_STACK_DEPTH];
+    __device__ __forceinline__ void put(int i, uint2 v) { e[i] = v; }
+    __device__ __forceinline__ uint2 get(int i) const { return e[i]; }
+};
 template <int D, int THREADS>
 struct TravHybridStack {
+    static constexpr bool compact = false;
     uint4 e[WRT_STACK_DEPTH - D];
     uint4* column;  // shared memory: this thread's entry 0; entry i is column[i * THREADS]
     __device__ __forceinline__ void put(int i, uint4 v) { if (i < D) column[i * THREADS] = v; else e[i - D] = v; }
@@ -765,12 +785,53 @@ __device__ __forceinline__ void trav_node4_step(const DeviceScene& S, TR& T, STK
     T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
 }
 
+// The same step with compact stack entries (TravCompactStack): the sort carries (key, child word) pairs.
+template <class TR, class STK>
+__device__ __forceinline__ void trav_node4_step_compact(const DeviceScene& S, TR& T, STK& stack) {
+    const float4* p = reinterpret_cast<const float4*>(S.nodes4 + T.node);
+    float4 lox, loy, loz, hix, hiy, hiz;
+    uint4 desc, end;
+    ldg256(p, lox, loy); ldg256(p + 2, loz, hix); ldg256(p + 4, hiy, hiz); ldg256(p + 6, desc, end);
+    const float t_hi = __double2float_ru(T.best_t);
+    float e0, e1, e2, e3;
+    const bool h0 = T.cull.entry(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, T.t_lo, t_hi, e0) && desc.x != WRT_NONE;
+    const bool h1 = T.cull.entry(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, T.t_lo, t_hi, e1) && desc.y != WRT_NONE;
+    const bool h2 = T.cull.entry(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, T.t_lo, t_hi, e2) && desc.z != WRT_NONE;
+    const bool h3 = T.cull.entry(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, T.t_lo, t_hi, e3) && desc.w != WRT_NONE;
+    const uint32_t miss = 0x7F800000u;  // +inf: sorts last
+    uint32_t k0 = h0 ? ((__float_as_uint(fmaxf(e0, 0.0f)) & ~3u) | 0u) : (miss | 0u);
+    uint32_t k1 = h1 ? ((__float_as_uint(fmaxf(e1, 0.0f)) & ~3u) | 1u) : (miss | 1u);
+    uint32_t k2 = h2 ? ((__float_as_uint(fmaxf(e2, 0.0f)) & ~3u) | 2u) : (miss | 2u);
+    uint32_t k3 = h3 ? ((__float_as_uint(fmaxf(e3, 0.0f)) & ~3u) | 3u) : (miss | 3u);
+    // child word: the record of an inner child, the primitive (kind + index, from `end`) of a leaf
+    uint32_t m0 = (desc.x & 0x80000000u) ? desc.x : (end.x & 0x7FFFFFFFu);
+    uint32_t m1 = (desc.y & 0x80000000u) ? desc.y : (end.y & 0x7FFFFFFFu);
+    uint32_t m2 = (desc.z & 0x80000000u) ? desc.z : (end.z & 0x7FFFFFFFu);
+    uint32_t m3 = (desc.w & 0x80000000u) ? desc.w : (end.w & 0x7FFFFFFFu);
+#define WRT_CSWAP2(ka, ma, kb, mb) { const bool sw_ = ka > kb; const uint32_t klo_ = sw_ ? kb : ka, khi_ = sw_ ? ka : kb, mlo_ = sw_ ? mb : ma, mhi_ = sw_ ? ma : mb; ka = klo_; kb = khi_; ma = mlo_; mb = mhi_; }
+    WRT_CSWAP2(k0, m0, k1, m1) WRT_CSWAP2(k2, m2, k3, m3) WRT_CSWAP2(k0, m0, k2, m2) WRT_CSWAP2(k1, m1, k3, m3) WRT_CSWAP2(k1, m1, k2, m2)
+#undef WRT_CSWAP2
+    if (k3 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m3, k3));
+    if (k2 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m2, k2));
+    if (k1 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m1, k1));
+    if (k0 < miss) {
+        if (m0 & 0x80000000u) { T.node = m0 & 0x7FFFFFFFu; }
+        else { T.node = WRT_NONE; T.pc = WRT_PC_UNKNOWN; T.end = WRT_LEAF_PRIM | m0; }
+        return;
+    }
+    T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
+}
+
 // WIDE: 0 = child-pair records, 1 = four-wide records (the hot kernels are instantiated for the form the scene uses: a run-time
 // switch inside the per-lane megakernel's record loop cost the 484-sphere scene 7 %), 2 = ask the scene (gates, diagnostics)
 template <int WIDE = 2, class TR, class STK>
 __device__ __forceinline__ void trav_record_step(const DeviceScene& S, TR& T, STK& stack) {
-    if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
-    else trav_node_step(S, T, stack);
+    if constexpr (STK::compact) {
+        trav_node4_step_compact(S, T, stack);
+    } else {
+        if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
+        else trav_node_step(S, T, stack);
+    }
 }
 
 // One op of the current leaf range (T.pc < T.end).
@@ -787,7 +848,9 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, S
     d3 o, d;
     trav_local_ray(S, T, world, o, d);
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
-        if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint4(op.z, T.end, T.xf, 0u));
+        if constexpr (!STK::compact) {  // (a compact-stack scene is one tree: nothing follows the root in its range)
+            if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint4(op.z, T.end, T.xf, 0u));
+        }
         T.node = S.use_wide ? __ldg(S.root4 + op.y) : op.y;
     } else if (op.x == OP_NODE_TIGHT_ONLY) {
         T.pc = T.cull.pass(S, op.y, tmin, T.best_t) ? pc + 1 : op.z;
@@ -811,8 +874,10 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, S
             double root = (h - sq) / a;
             if (!(tmin < root)) root = (h + sq) / a;  // the near root is unusable: the reference then tries the far one
             if ((tmin < root) && (root <= T.best_t) && (root < tmax)) {
-                if (root < T.best_t) { T.best_t = root; T.first_pc = pc; T.first_xf = T.xf; T.lastq_pc = WRT_NONE; }
-                else if (pc < T.first_pc) { T.first_pc = pc; T.first_xf = T.xf; }
+                uint32_t hp = pc;  // program position of the primitive (compact entries do not carry it)
+                if constexpr (STK::compact) { if (pc == WRT_PC_UNKNOWN) hp = __ldg(S.sphere_pc + op.y); }
+                if (root < T.best_t) { T.best_t = root; T.first_pc = hp; T.first_xf = T.xf; T.lastq_pc = WRT_NONE; }
+                else if (hp < T.first_pc) { T.first_pc = hp; T.first_xf = T.xf; }
             }
         }
         T.pc = pc + 1;
@@ -830,10 +895,12 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, S
                 d3 p = o + d * t;
                 d3 planar = p - mk(s0.x, s0.y, s1.x);
                 if (quad_interior(g, planar)) {
-                    if (t < T.best_t) { T.best_t = t; T.first_pc = pc; T.first_xf = T.xf; T.lastq_pc = pc; T.lastq_xf = T.xf; }
+                    uint32_t hp = pc;
+                    if constexpr (STK::compact) { if (pc == WRT_PC_UNKNOWN) hp = __ldg(S.quad_pc + op.y); }
+                    if (t < T.best_t) { T.best_t = t; T.first_pc = hp; T.first_xf = T.xf; T.lastq_pc = hp; T.lastq_xf = T.xf; }
                     else {
-                        if (pc < T.first_pc) { T.first_pc = pc; T.first_xf = T.xf; }
-                        if (T.lastq_pc == WRT_NONE || pc > T.lastq_pc) { T.lastq_pc = pc; T.lastq_xf = T.xf; }
+                        if (hp < T.first_pc) { T.first_pc = hp; T.first_xf = T.xf; }
+                        if (T.lastq_pc == WRT_NONE || hp > T.lastq_pc) { T.lastq_pc = hp; T.lastq_xf = T.xf; }
                     }
                 }
             }
@@ -860,6 +927,17 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, S
 // empty (the traversal is complete).
 template <class TR, class STK, typename WORLD>
 __device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, STK& stack, WORLD&& world) {
+    if constexpr (STK::compact) {
+        (void)world;
+        while (T.sp > 0) {
+            const uint2 e = stack.get(--T.sp);
+            if (__uint_as_float(e.y & ~3u) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
+            if (e.x & 0x80000000u) { T.node = e.x & 0x7FFFFFFFu; }
+            else { T.node = WRT_NONE; T.pc = WRT_PC_UNKNOWN; T.end = WRT_LEAF_PRIM | e.x; }
+            return false;
+        }
+        return true;
+    } else {
     while (T.sp > 0) {
         const uint4 e = stack.get(--T.sp);
         if (__uint_as_float(e.w) > __double2float_ru(T.best_t)) continue;  // its box now starts beyond the closest hit
@@ -877,6 +955,7 @@ __device__ __forceinline__ bool trav_pop_lazy(const DeviceScene& S, TR& T, STK& 
         return false;
     }
     return true;
+    }
 }
 
 // One op of the current leaf range (if any is left), then — when that exhausted the range — the pop, so a single-primitive

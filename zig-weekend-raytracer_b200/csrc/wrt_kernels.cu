@@ -1212,7 +1212,7 @@ __device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& 
 
 template <int N> struct WfStackColumns { __device__ __forceinline__ static uint4* get() { __shared__ uint4 a[N * 128]; return a; } };
 template <> struct WfStackColumns<0> { __device__ __forceinline__ static uint4* get() { return nullptr; } };
-template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS, int SMSTACK = 0>
+template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS, int SMSTACK = 0, bool COMPACT = false>
 __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     __shared__ WfStage stage[4];  // one per warp of the block
     // SMSTACK > 0 keeps the bottom entries of every thread's stack in shared memory.  Measured on C5 (8 blocks / SM): 0 / 4 / 6 / 8
@@ -1233,7 +1233,8 @@ __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __gr
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t chunk = max(32u, min((uint32_t)WRT_WF_CURSOR_CHUNK, (n / (2u * n_warps)) & ~31u));
     TravLean T;  // the local ray is re-formed from the path record where a leaf op needs it
-    typename std::conditional<SMSTACK != 0, TravHybridStack<(SMSTACK ? SMSTACK : 1), 128>, TravLocalStack>::type stack;
+    typename std::conditional<COMPACT, TravCompactStack,
+                              typename std::conditional<SMSTACK != 0, TravHybridStack<(SMSTACK ? SMSTACK : 1), 128>, TravLocalStack>::type>::type stack;
     if constexpr (SMSTACK != 0) stack.column = stack_columns + threadIdx.x;
     uint32_t slot = 0;
     bool has = false, drained = false;
@@ -1574,7 +1575,9 @@ cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, 
     if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)
         if (S.use_wide) {
             const int b = wf_extend_min_blocks();
-            if (b == 8) wf_extend_ordered_kernel<1, 8><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            if (S.compact_ok && b >= 7) wf_extend_ordered_kernel<1, 8, 0, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            else if (S.compact_ok) wf_extend_ordered_kernel<1, 6, 0, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            else if (b == 8) wf_extend_ordered_kernel<1, 8><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
             else if (b == 7) wf_extend_ordered_kernel<1, 7><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
             else wf_extend_ordered_kernel<1><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
         }

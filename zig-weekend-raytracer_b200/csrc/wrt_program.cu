@@ -201,6 +201,11 @@ struct Compiler {
                 const uint32_t mat = sphere ? sc->spheres[e.a].material : sc->quads[e.a].material;
                 if (mat >= sc->n_materials) { ok = fail(WRT_E_INVALID, "material index out of range"); break; }
                 if (prim_id[id] == WRT_NONE) prim_id[id] = out.n_prims++;
+                {  // the op that tests this primitive record (compact stack entries look it up on a hit); one op only, or no compact form
+                    std::vector<uint32_t>& table = sphere ? out.sphere_pc : out.quad_pc;
+                    if (table[e.a] == WRT_NONE) table[e.a] = (uint32_t)out.ops.size();
+                    else out.prim_pc_unique = false;
+                }
                 out.ops.push_back(make_uint4(sphere ? OP_SPHERE : OP_QUAD, e.a, mat, prim_id[id]));
                 break;
             }
@@ -530,6 +535,8 @@ struct Compiler {
             out.nodes2.reserve(n_nodes + n_xf + 1);
             out.xforms.reserve(n_xf);
         }
+        out.sphere_pc.assign(std::max<size_t>(sc->n_spheres, 1), WRT_NONE);
+        out.quad_pc.assign(std::max<size_t>(sc->n_quads, 1), WRT_NONE);
         if (!emit(sc->root, WRT_NONE, 0)) return code;
         out.ops.push_back(make_uint4(OP_END, 0, 0, 0));
         const auto t2 = now();
@@ -704,6 +711,17 @@ void finish_trees(CompiledScene& out) {
     const char* force_wide = std::getenv("WRT_WIDE_TREE");  // A/B switch: 0 / 1 overrides the size rule
     out.use_wide = force_wide ? (force_wide[0] == '1') : (out.nodes2.size() >= WRT_WIDE_TREE_MIN_RECORDS);
     out.stack_depth = ordered_stack_depth(out);
+    // compact stack entries (wrt_device.cuh: TravCompactStack): one tree whose root op spans the program, no transforms, every
+    // leaf of the four-wide records a single primitive, every primitive record tested by exactly one op
+    out.compact_ok = false;
+    if (out.use_wide && out.prim_pc_unique && out.xforms.empty() && out.tree_inputs.size() == 1 && out.ops.size() >= 2 &&
+        out.ops[0].x == OP_NODE && out.ops[0].z == out.ops.size() - 1 && !out.has_moving) {
+        bool ok = true;
+        for (const Node4& n : out.nodes4)
+            for (int i = 0; i < 4 && ok; ++i)
+                if (n.desc[i] != WRT_NONE && !(n.desc[i] & 0x80000000u) && !(n.end[i] & WRT_LEAF_PRIM)) ok = false;
+        out.compact_ok = ok;
+    }
     out.trees_built = true;
 }
 

@@ -35,6 +35,9 @@ struct CompiledScene {
     std::vector<Texture> textures;
     std::vector<Light> lights;
     std::vector<BoxTight> light_boxes;  // conservative binary32 box of every light (an empty box for kinds whose pdf is 0)
+    std::vector<uint32_t> sphere_pc, quad_pc;  // per primitive record: the op that tests it (WRT_NONE: unused record)
+    bool prim_pc_unique = true;                // no primitive record is tested by two ops
+    bool compact_ok = false;                   // the scene qualifies for compact stack entries (set with the trees)
     std::vector<TreeInput> tree_inputs;  // per reference BVH, program order; consumed (reordered) by the tree build
     bool trees_built = false;            // nodes2 / nodes4 / root4 / use_wide / stack_depth are final
     uint32_t n_prims = 0;
