@@ -277,6 +277,8 @@ typedef struct wrt_scene_info {
     uint32_t n_lights;
     uint32_t ref_boxes_loose;/* bvh_node boxes that do not contain their subtree in x / y (0 => AUTO culling = TIGHT) */
     uint32_t stack_depth;    /* exact worst-case stack use of the ordered traversal on the rebuilt trees */
+    uint32_t compact_stack;  /* 1: one tree of single-primitive leaves without transforms — the wavefront's extend kernel uses 8-byte stack entries */
+    uint32_t quantised_records; /* number of 64-byte quantised four-wide records (0: the scene walks the binary32 records) */
 } wrt_scene_info;
 WRT_API int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, char* err, size_t err_cap);
 

@@ -56,7 +56,7 @@ def test_ctypes_mirror_matches_c_layout(wrt, tmp_path):
                                     "clear_color", "seed", "row_shard_index", "row_shard_count", "sample_begin", "sample_end",
                                     "cull_mode", "flags"]),
         "wrt_scene_info": (wrt.SceneInfo, ["n_ops", "n_ops_packet", "n_prims", "n_boxes", "n_tree_records", "tree_depth", "max_nesting",
-                                           "n_lights", "ref_boxes_loose", "stack_depth"]),
+                                           "n_lights", "ref_boxes_loose", "stack_depth", "compact_stack", "quantised_records"]),
         "wrt_stats": (wrt.Stats, ["paths", "rays", "render_ms", "kernel_ms", "upload_ms", "kernel_launches", "program_ops",
                                   "n_prims", "cull_mode_used", "traversal_steps", "ref_boxes_loose", "n_devices", "gather_ms",
                                   "kernel_ms_min", "kernel_ms_max", "tree_build_ms", "tree_build_device", "n_tree_records"]),

@@ -85,3 +85,18 @@ def test_host_tree_build_is_deterministic_and_survives_coincident_centroids(wrt,
     info = wrt.check_scene(flat)
     assert info.tree_depth <= 64
     sc.close()
+
+
+def test_compact_form_is_offered_only_to_flat_single_tree_scenes(wrt, wro, images):
+    """Compact stack entries + quantised four-wide records (wrt_device.cuh: TravCompactStack, Node4Q) need one tree of
+    single-primitive leaves, no transforms and a primitive -> op table that inverts the program; wrt_check_scene verifies the
+    tables and that every quantised box contains (by less than one step) the binary32 box it stands for."""
+    sc = wro.OracleScene("synthetic", seed=2, n_prims=50000)
+    info = wrt.check_scene(sc.flatten())
+    assert info.compact_stack == 1 and info.quantised_records == info.n_tree_records > 0
+    sc.close()
+    for name in ("cornell_box", "balls", "rtw_final"):     # small (child-pair records) or instanced scenes keep the general form
+        sc = wro.OracleScene(name, seed=1, images=images)
+        info = wrt.check_scene(sc.flatten())
+        assert info.compact_stack == 0 and info.quantised_records == 0
+        sc.close()

@@ -97,7 +97,8 @@ class Params(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_ops", C.c_uint32), ("n_ops_packet", C.c_uint32), ("n_prims", C.c_uint32), ("n_boxes", C.c_uint32),
                 ("n_tree_records", C.c_uint32), ("tree_depth", C.c_uint32), ("max_nesting", C.c_uint32), ("n_lights", C.c_uint32),
-                ("ref_boxes_loose", C.c_uint32), ("stack_depth", C.c_uint32)]
+                ("ref_boxes_loose", C.c_uint32), ("stack_depth", C.c_uint32), ("compact_stack", C.c_uint32),
+                ("quantised_records", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -95,6 +95,8 @@ extern "C" int wrt_check_scene(const wrt_scene* scene, wrt_scene_info* info, cha
     info->n_lights = (uint32_t)cs.lights.size();
     info->ref_boxes_loose = cs.ref_boxes_loose;
     info->stack_depth = cs.stack_depth;
+    info->compact_stack = cs.compact_ok ? 1u : 0u;
+    info->quantised_records = (uint32_t)cs.nodes4q.size();
     if (!wrt::check_compiled_scene(cs, info->tree_depth, msg)) { report(msg); return WRT_E_STATE; }
     return WRT_OK;
 }
@@ -196,7 +198,7 @@ extern "C" void wrt_destroy(wrt_ctx* ctx) {
     wrt::comm_release(ctx);
     ctx->d_shard.release(); ctx->d_staging.release();
     ctx->free_images();
-    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_nodes4.release(); ctx->d_root4.release(); ctx->d_sphere_pc.release(); ctx->d_quad_pc.release(); ctx->d_spheres.release();
+    ctx->d_ops.release(); ctx->d_ops_pruned.release(); ctx->d_boxes_ref.release(); ctx->d_boxes_tight.release(); ctx->d_nodes2.release(); ctx->d_nodes4.release(); ctx->d_root4.release(); ctx->d_sphere_pc.release(); ctx->d_quad_pc.release(); ctx->d_nodes4q.release(); ctx->d_spheres.release();
     ctx->d_sphere_aux.release(); ctx->d_quads.release(); ctx->d_xforms.release(); ctx->d_xform_chains.release(); ctx->d_materials.release();
     ctx->d_textures.release(); ctx->d_images.release(); ctx->d_lights.release(); ctx->d_light_boxes.release(); ctx->d_sobol_matrices.release(); ctx->d_sobol_lut.release();
     ctx->d_accum.release(); ctx->d_fb.release(); ctx->d_rgb8.release(); ctx->d_counters.release();
@@ -292,6 +294,7 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     CU(ctx->d_root4.upload(cs.root4, ctx->stream));
     CU(ctx->d_sphere_pc.upload(cs.sphere_pc, ctx->stream));
     CU(ctx->d_quad_pc.upload(cs.quad_pc, ctx->stream));
+    CU(ctx->d_nodes4q.upload(cs.nodes4q, ctx->stream));
     CU(ctx->d_spheres.upload(cs.spheres, ctx->stream));
     CU(ctx->d_sphere_aux.upload(cs.sphere_aux, ctx->stream));
     CU(ctx->d_quads.upload(cs.quads, ctx->stream));
@@ -318,6 +321,8 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     {
         const char* env = std::getenv("WRT_COMPACT_STACK");  // A/B switch: 0 keeps the 16-byte entries
         ds.compact_ok = (cs.compact_ok && !(env && env[0] == '0')) ? 1u : 0u;
+        const char* envq = std::getenv("WRT_QUANT_RECORDS");  // A/B switch: 0 keeps the binary32 records under the compact stack
+        ds.nodes4q = (ds.compact_ok && !cs.nodes4q.empty() && !(envq && envq[0] == '0')) ? ctx->d_nodes4q.p : nullptr;
     }
     ctx->ds_pruned = ds;
     if (!cs.ops_pruned.empty()) { ctx->ds_pruned.ops = ctx->d_ops_pruned.p; ctx->ds_pruned.n_ops = (uint32_t)cs.ops_pruned.size(); }
@@ -666,6 +671,9 @@ int wrt::render_impl(wrt_ctx* ctx, const wrt_camera* cam, const wrt_params* para
             A[k].sort_tmp = sort_buckets ? ctx->d_wf_sort_tmp.p + first_slot : nullptr;
             A[k].sort_hist = sort_buckets ? ctx->d_wf_sort_hist.p + (size_t)k * sort_buckets : nullptr;
             A[k].sort_buckets = sort_buckets; A[k].sort_shift = sort_shift;
+            auto env_u = [](const char* name) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : 0u; };
+            A[k].node_burst = env_u("WRT_WF_NODE_BURST"); A[k].leaf_burst = env_u("WRT_WF_LEAF_BURST");
+            A[k].node_shift = std::getenv("WRT_WF_NODE_SHIFT") ? env_u("WRT_WF_NODE_SHIFT") + 1u : 0u;
             wf_grid[k] = (uint32_t)std::min<uint64_t>((cap + 255) / 256, (uint64_t)ctx->sm_count * 8);
             first_slot += cap;
         }

@@ -73,6 +73,7 @@ struct wrt_ctx {
     wrt::DevBuf<wrt::Node4> d_nodes4;
     wrt::DevBuf<uint32_t> d_root4;
     wrt::DevBuf<uint32_t> d_sphere_pc, d_quad_pc;
+    wrt::DevBuf<wrt::Node4Q> d_nodes4q;
     wrt::DevBuf<wrt::SphereGeom> d_spheres;
     wrt::DevBuf<wrt::SphereAux> d_sphere_aux;
     wrt::DevBuf<wrt::QuadGeom> d_quads;

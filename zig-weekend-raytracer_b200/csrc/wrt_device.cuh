@@ -82,6 +82,20 @@ struct __align__(16) Node4 {
     uint32_t desc[4];
     uint32_t end[4];
 };
+// Quantised four-wide record (64 bytes, two 256-bit loads): the children's boxes as 8-bit offsets from the record's own
+// box, lo rounded down and hi rounded up so that the decoded box contains the binary32 box of Node4; child words as in the
+// compact stack entries (inner: bit 31 + record index, leaf: kind bit 30 + primitive record index, WRT_NONE: empty).  Only
+// for scenes with DeviceScene::compact_ok.  Half the L1 tag cycles per step and half the record bytes in L1 / L2.
+struct __align__(32) Node4Q {
+    float ox, oy, oz;      // min corner of the union of the children's boxes
+    uint32_t exps;         // byte k: biased binary32 exponent of the step of axis k (step = 2^(e - 127))
+    uint32_t qlo[3];       // per axis: byte i = child i's lo, in steps from the corner (rounded down)
+    uint32_t qhi[3];       // ... hi (rounded up)
+    uint32_t word[4];
+    uint32_t _pad[2];
+};
+static_assert(sizeof(Node4Q) == 64, "Node4Q is two 256-bit loads");
+
 struct __align__(16) SphereGeom { // entity.zig:536-537
     double cx, cy, cz, radius;
 };
@@ -144,6 +158,7 @@ struct DeviceScene {
     const Light* lights;
     const BoxTight* light_boxes;  // parallel to lights
     uint32_t n_ops, n_lights, has_lights, has_moving;
+    const Node4Q* nodes4q;      // compact_ok scenes: nodes4 in quantised form (same indices)
     const uint32_t* sphere_pc;  // per sphere / quad record: the op that tests it (compact stack entries, see TravCompactStack)
     const uint32_t* quad_pc;
     uint32_t compact_ok;   // one tree of single-primitive leaves, no transforms, every primitive tested by exactly one op
@@ -644,6 +659,7 @@ __device__ inline ClosestHit closest_hit(const DeviceScene& S, d3 wo, d3 wd, dou
 // lanes at different depths do not conflict), the rest in local memory.
 struct TravLocalStack {
     static constexpr bool compact = false;
+    static constexpr bool quant = false;
     uint4 e[WRT_STACK_DEPTH];
     __device__ __forceinline__ void put(int i, uint4 v) { e[i] = v; }
     __device__ __forceinline__ uint4 get(int i) const { return e[i]; }
@@ -659,6 +675,7 @@ struct TravLocalStack {
 #define WRT_PC_UNKNOWN 0x7FFFFFF0u
 struct TravCompactStack {
     static constexpr bool compact = true;
+    static constexpr bool quant = false;
     uint2 e[WRT_STACK_DEPTH];
     __device__ __forceinline__ void put(int i, uint2 v) { e[i] = v; }
     __device__ __forceinline__ uint2 get(int i) const { return e[i]; }
@@ -666,10 +683,15 @@ struct TravCompactStack {
 template <int D, int THREADS>
 struct TravHybridStack {
     static constexpr bool compact = false;
+    static constexpr bool quant = false;
     uint4 e[WRT_STACK_DEPTH - D];
     uint4* column;  // shared memory: this thread's entry 0; entry i is column[i * THREADS]
     __device__ __forceinline__ void put(int i, uint4 v) { if (i < D) column[i * THREADS] = v; else e[i - D] = v; }
     __device__ __forceinline__ uint4 get(int i) const { return (i < D) ? column[i * THREADS] : e[i - D]; }
+};
+
+struct TravCompactStackQ : TravCompactStack {  // compact entries, and the records are read in their quantised form (Node4Q)
+    static constexpr bool quant = true;
 };
 
 // LEAN: the binary64 ray in the current transform context is NOT kept in the state (12 registers that are dead weight while
@@ -822,11 +844,55 @@ __device__ __forceinline__ void trav_node4_step_compact(const DeviceScene& S, TR
     T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
 }
 
+// The compact step over quantised records.  A slab distance is (corner + q * step) * inv - o * inv = q * (step * inv) +
+// (corner * inv - o * inv): `step` is a power of two, so step * inv is exact, and the bracket is one FMA — one rounding more
+// than Culler::entry's, of size (|corner * inv| + |o * inv|) * 2^-24, a quarter of the slack its margins leave (see there).
+template <class TR, class STK>
+__device__ __forceinline__ void trav_node4q_step_compact(const DeviceScene& S, TR& T, STK& stack) {
+    const float4* p = reinterpret_cast<const float4*>(S.nodes4q + T.node);
+    uint4 a, b, c, w;
+    ldg256(p, a, b); ldg256(p + 2, c, w);  // a = (ox, oy, oz, exps)  b = (qlo x, y, z, qhi x)  c = (qhi y, z, word0, word1)  w = (word2, word3, -, -)
+    const auto& cu = T.cull;
+    const float sx = __uint_as_float((a.w & 0xFFu) << 23) * cu.inv_x, sy = __uint_as_float(((a.w >> 8) & 0xFFu) << 23) * cu.inv_y,
+                sz = __uint_as_float(((a.w >> 16) & 0xFFu) << 23) * cu.inv_z;
+    const float bx = fmaf(__uint_as_float(a.x), cu.inv_x, -cu.oi_x), by = fmaf(__uint_as_float(a.y), cu.inv_y, -cu.oi_y),
+                bz = fmaf(__uint_as_float(a.z), cu.inv_z, -cu.oi_z);
+    const float t_hi = __double2float_ru(T.best_t);
+    const uint32_t word[4] = {c.z, c.w, w.x, w.y};
+    const uint32_t miss = 0x7F800000u;  // +inf: sorts last
+    uint32_t k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float lx = fmaf((float)((b.x >> (8 * i)) & 0xFFu), sx, bx), hx = fmaf((float)((b.w >> (8 * i)) & 0xFFu), sx, bx);
+        const float ly = fmaf((float)((b.y >> (8 * i)) & 0xFFu), sy, by), hy = fmaf((float)((c.x >> (8 * i)) & 0xFFu), sy, by);
+        const float lz = fmaf((float)((b.z >> (8 * i)) & 0xFFu), sz, bz), hz = fmaf((float)((c.y >> (8 * i)) & 0xFFu), sz, bz);
+        const float lo = fmaxf(fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fminf(lz, hz)) - cu.err, T.t_lo);
+        const float hi = fminf(fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fmaxf(lz, hz)) + cu.err, t_hi);
+        const bool hit = (hi * 1.000002f + 1e-30f >= lo) && word[i] != WRT_NONE;
+        k[i] = hit ? ((__float_as_uint(fmaxf(lo, 0.0f)) & ~3u) | (uint32_t)i) : (miss | (uint32_t)i);
+    }
+    uint32_t k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3], m0 = word[0], m1 = word[1], m2 = word[2], m3 = word[3];
+#define WRT_CSWAP2(ka, ma, kb, mb) { const bool sw_ = ka > kb; const uint32_t klo_ = sw_ ? kb : ka, khi_ = sw_ ? ka : kb, mlo_ = sw_ ? mb : ma, mhi_ = sw_ ? ma : mb; ka = klo_; kb = khi_; ma = mlo_; mb = mhi_; }
+    WRT_CSWAP2(k0, m0, k1, m1) WRT_CSWAP2(k2, m2, k3, m3) WRT_CSWAP2(k0, m0, k2, m2) WRT_CSWAP2(k1, m1, k3, m3) WRT_CSWAP2(k1, m1, k2, m2)
+#undef WRT_CSWAP2
+    if (k3 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m3, k3));
+    if (k2 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m2, k2));
+    if (k1 < miss && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint2(m1, k1));
+    if (k0 < miss) {
+        if (m0 & 0x80000000u) { T.node = m0 & 0x7FFFFFFFu; }
+        else { T.node = WRT_NONE; T.pc = WRT_PC_UNKNOWN; T.end = WRT_LEAF_PRIM | m0; }
+        return;
+    }
+    T.node = WRT_NONE; T.pc = 0; T.end = 0;  // nothing hit: the caller pops
+}
+
 // WIDE: 0 = child-pair records, 1 = four-wide records (the hot kernels are instantiated for the form the scene uses: a run-time
 // switch inside the per-lane megakernel's record loop cost the 484-sphere scene 7 %), 2 = ask the scene (gates, diagnostics)
 template <int WIDE = 2, class TR, class STK>
 __device__ __forceinline__ void trav_record_step(const DeviceScene& S, TR& T, STK& stack) {
-    if constexpr (STK::compact) {
+    if constexpr (STK::compact && STK::quant) {
+        trav_node4q_step_compact(S, T, stack);
+    } else if constexpr (STK::compact) {
         trav_node4_step_compact(S, T, stack);
     } else {
         if (WIDE == 1 || (WIDE == 2 && S.use_wide)) trav_node4_step(S, T, stack);
@@ -844,9 +910,16 @@ __device__ __forceinline__ void trav_leaf_op_lazy(const DeviceScene& S, TR& T, S
         T.end = pc + 1;                                                                                   // load) is skipped
     } else {
         op = __ldg(S.ops + pc);
+        if constexpr (STK::compact) {  // a compact-stack scene is one tree: the only op ever read is its root, at pc 0
+            T.node = __ldg(S.root4 + op.y);
+            return;
+        }
     }
     d3 o, d;
     trav_local_ray(S, T, world, o, d);
+    if constexpr (STK::compact) {  // only the two primitive kinds reach this point, and there is no transform context
+        if (op.x != OP_SPHERE) op.x = OP_QUAD;
+    }
     if (op.x == OP_NODE) {  // a bvh subtree inside this range: descend it ordered, come back for the rest of the range
         if constexpr (!STK::compact) {  // (a compact-stack scene is one tree: nothing follows the root in its range)
             if (op.z < T.end && T.sp < WRT_STACK_DEPTH) stack.put(T.sp++, make_uint4(op.z, T.end, T.xf, 0u));

@@ -1212,7 +1212,7 @@ __device__ __forceinline__ void wf_stage_flush(const WavefrontArgs& A, WfStage& 
 
 template <int N> struct WfStackColumns { __device__ __forceinline__ static uint4* get() { __shared__ uint4 a[N * 128]; return a; } };
 template <> struct WfStackColumns<0> { __device__ __forceinline__ static uint4* get() { return nullptr; } };
-template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS, int SMSTACK = 0, bool COMPACT = false>
+template <int WIDE, int MINB = WRT_WF_EXTEND_MIN_BLOCKS, int SMSTACK = 0, bool COMPACT = false, bool QUANT = false>
 __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __grid_constant__ LaunchParams LP, WavefrontArgs A, DeviceScene S, uint32_t parity) {
     __shared__ WfStage stage[4];  // one per warp of the block
     // SMSTACK > 0 keeps the bottom entries of every thread's stack in shared memory.  Measured on C5 (8 blocks / SM): 0 / 4 / 6 / 8
@@ -1232,8 +1232,10 @@ __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __gr
     // chunk: a few draws per warp on a full queue, but never so large that a short queue lands on a handful of warps
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t chunk = max(32u, min((uint32_t)WRT_WF_CURSOR_CHUNK, (n / (2u * n_warps)) & ~31u));
+    const int node_burst = A.node_burst ? (int)A.node_burst : WRT_WF_NODE_BURST, leaf_burst = A.leaf_burst ? (int)A.leaf_burst : WRT_WF_LEAF_BURST;
+    const int node_shift = A.node_shift ? (int)A.node_shift - 1 : WRT_WF_NODE_SHIFT;  // (stored + 1 so that 0 means default)
     TravLean T;  // the local ray is re-formed from the path record where a leaf op needs it
-    typename std::conditional<COMPACT, TravCompactStack,
+    typename std::conditional<COMPACT, typename std::conditional<QUANT, TravCompactStackQ, TravCompactStack>::type,
                               typename std::conditional<SMSTACK != 0, TravHybridStack<(SMSTACK ? SMSTACK : 1), 128>, TravLocalStack>::type>::type stack;
     if constexpr (SMSTACK != 0) stack.column = stack_columns + threadIdx.x;
     uint32_t slot = 0;
@@ -1284,16 +1286,16 @@ __global__ void __launch_bounds__(128, MINB) wf_extend_ordered_kernel(const __gr
         // ---- node phase: box records, while at least half of the lanes that hold a ray stand on one ----
         const int n_has = __popc(__ballot_sync(0xffffffffu, has));
 #pragma unroll 1
-        for (int k = 0; k < WRT_WF_NODE_BURST; ++k) {
+        for (int k = 0; k < node_burst; ++k) {
             const bool in_node = has && T.node != WRT_NONE;
             const int n_node = __popc(__ballot_sync(0xffffffffu, in_node));
-            if (n_node == 0 || (k > 0 && (n_node << WRT_WF_NODE_SHIFT) < n_has)) break;
+            if (n_node == 0 || (k > 0 && (n_node << node_shift) < n_has)) break;
             if (in_node) { trav_record_step<WIDE>(S, T, stack); ++steps; }
         }
         // ---- leaf phase: ops of leaf ranges (binary64 primitive tests, transforms, nested roots) and pops, for the others ----
         bool done = false;
 #pragma unroll 1
-        for (int k = 0; k < WRT_WF_LEAF_BURST; ++k) {
+        for (int k = 0; k < leaf_burst; ++k) {
             const bool in_leaf = has && !done && T.node == WRT_NONE;
             if (!__any_sync(0xffffffffu, in_leaf)) break;
             if (in_leaf) { done = trav_leaf_step_lazy(S, T, stack, world_ray, 1e-4, CUDART_INF); ++steps; }
@@ -1575,7 +1577,8 @@ cudaError_t wf_launch_iteration(const LaunchParams& lp, const WavefrontArgs& A, 
     if (ordered) {  // persistent lanes with ray replacement (one wave of resident blocks)
         if (S.use_wide) {
             const int b = wf_extend_min_blocks();
-            if (S.compact_ok && b >= 7) wf_extend_ordered_kernel<1, 8, 0, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            if (S.compact_ok && S.nodes4q && b >= 7) wf_extend_ordered_kernel<1, 8, 0, true, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
+            else if (S.compact_ok && b >= 7) wf_extend_ordered_kernel<1, 8, 0, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
             else if (S.compact_ok) wf_extend_ordered_kernel<1, 6, 0, true><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
             else if (b == 8) wf_extend_ordered_kernel<1, 8><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);
             else if (b == 7) wf_extend_ordered_kernel<1, 7><<<persist_grid, 128, 0, stream>>>(lp, A, S, parity);

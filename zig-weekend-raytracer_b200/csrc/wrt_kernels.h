@@ -81,6 +81,9 @@ struct WavefrontArgs {
     uint32_t* sort_hist;          // [sort_buckets]
     uint32_t sort_buckets;
     uint32_t sort_shift;          // key = ((hit op >> sort_shift) << 3) | direction octant
+    // phase constants of the persistent extend kernel (0 = the compiled defaults; WRT_WF_NODE_BURST / _LEAF_BURST / _NODE_SHIFT in
+    // the environment override them for sweeps)
+    uint32_t node_burst, leaf_burst, node_shift;
 };
 enum { WS_JOB_CURSOR = 0, WS_JOBS_DONE = 1, WS_RAYS = 2, WS_PATHS = 3, WS_STEPS = 4, WS_COUNT = 8 };
 

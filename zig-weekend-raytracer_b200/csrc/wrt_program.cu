@@ -17,6 +17,7 @@
 #include <new>
 #include <stdexcept>
 #include <system_error>
+#include <thread>
 
 #include "wrt_program.h"
 #include "wrt_treebuild.cuh"
@@ -722,6 +723,30 @@ void finish_trees(CompiledScene& out) {
                 if (n.desc[i] != WRT_NONE && !(n.desc[i] & 0x80000000u) && !(n.end[i] & WRT_LEAF_PRIM)) ok = false;
         out.compact_ok = ok;
     }
+    // ... and their records in quantised form (Node4Q), first levels on the host threads
+    out.nodes4q.clear();
+    if (out.compact_ok) {
+        out.nodes4q.resize(out.nodes4.size());
+        const size_t n = out.nodes4.size();
+        const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const unsigned parts = n >= 65536 ? hw : 1u;
+        std::vector<char> ok(parts, 1);
+        auto work = [&](unsigned part) {
+            const size_t lo = n * part / parts, hi = n * (part + 1) / parts;
+            for (size_t i = lo; i < hi; ++i)
+                if (!tb_node4q(out.nodes4[i], out.nodes4q[i])) { ok[part] = 0; return; }
+        };
+        std::vector<std::thread> threads;
+        try {
+            for (unsigned part = 1; part < parts; ++part) threads.emplace_back(work, part);
+        } catch (const std::system_error&) {  // no thread to be had: the parts not started run here
+            for (unsigned part = (unsigned)threads.size() + 1; part < parts; ++part) work(part);
+        }
+        work(0);
+        for (auto& th : threads) th.join();
+        for (char c : ok)
+            if (!c) out.nodes4q.clear();  // an axis that cannot be expressed: the scene keeps walking nodes4
+    }
     out.trees_built = true;
 }
 
@@ -791,6 +816,36 @@ bool check_compiled_scene(const CompiledScene& cs, uint32_t& tree_depth, std::st
             const uint4 op = cs.ops_pruned[pc];
             if ((op.x == OP_NODE || op.x == OP_NODE_TIGHT_ONLY) && !(op.z > pc && op.z <= np - 1)) {
                 err = "packet program: skip link out of range at op " + std::to_string(pc); return false;
+            }
+        }
+    }
+    // compact form (TravCompactStack / Node4Q): the primitive -> op tables invert the program, and every quantised box contains
+    // the binary32 box it stands for, with the child words of the record it was made from
+    if (cs.compact_ok) {
+        for (size_t pc = 0; pc < n; ++pc) {
+            const uint4 op = cs.ops[pc];
+            if (op.x == OP_SPHERE && (op.y >= cs.sphere_pc.size() || cs.sphere_pc[op.y] != pc)) { err = "sphere_pc does not invert the program at op " + std::to_string(pc); return false; }
+            if (op.x == OP_QUAD && (op.y >= cs.quad_pc.size() || cs.quad_pc[op.y] != pc)) { err = "quad_pc does not invert the program at op " + std::to_string(pc); return false; }
+        }
+        if (!cs.nodes4q.empty()) {
+            if (cs.nodes4q.size() != cs.nodes4.size()) { err = "nodes4q: record count differs from nodes4"; return false; }
+            for (size_t r = 0; r < cs.nodes4.size(); ++r) {
+                const Node4& a = cs.nodes4[r];
+                const Node4Q& q = cs.nodes4q[r];
+                const float* lo[3] = {a.lox, a.loy, a.loz};
+                const float* hi[3] = {a.hix, a.hiy, a.hiz};
+                const double o[3] = {q.ox, q.oy, q.oz};
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t want = a.desc[i] == WRT_NONE ? WRT_NONE : ((a.desc[i] & 0x80000000u) ? a.desc[i] : (a.end[i] & 0x7FFFFFFFu));
+                    if (q.word[i] != want) { err = "nodes4q: child word differs at record " + std::to_string(r); return false; }
+                    if (a.desc[i] == WRT_NONE) continue;
+                    for (int k = 0; k < 3; ++k) {
+                        const double step = std::ldexp(1.0, (int)((q.exps >> (8 * k)) & 0xFFu) - 127);
+                        const double dlo = o[k] + (double)((q.qlo[k] >> (8 * i)) & 0xFFu) * step, dhi = o[k] + (double)((q.qhi[k] >> (8 * i)) & 0xFFu) * step;
+                        if (!(dlo <= (double)lo[k][i] && dhi >= (double)hi[k][i])) { err = "nodes4q: decoded box does not contain the child's box at record " + std::to_string(r); return false; }
+                        if (!(dlo > (double)lo[k][i] - 1.0001 * step && dhi < (double)hi[k][i] + 1.0001 * step)) { err = "nodes4q: decoded box is more than one step loose at record " + std::to_string(r); return false; }
+                    }
+                }
             }
         }
     }

@@ -35,6 +35,7 @@ struct CompiledScene {
     std::vector<Texture> textures;
     std::vector<Light> lights;
     std::vector<BoxTight> light_boxes;  // conservative binary32 box of every light (an empty box for kinds whose pdf is 0)
+    std::vector<Node4Q> nodes4q;               // compact_ok scenes: nodes4 quantised (empty: not available)
     std::vector<uint32_t> sphere_pc, quad_pc;  // per primitive record: the op that tests it (WRT_NONE: unused record)
     bool prim_pc_unique = true;                // no primitive record is tested by two ops
     bool compact_ok = false;                   // the scene qualifies for compact stack entries (set with the trees)

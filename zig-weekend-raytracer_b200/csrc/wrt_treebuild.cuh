@@ -211,4 +211,59 @@ WRT_HD Node4 tb_node4(const TreeChild4* ch, int n, uint32_t first_child, const u
     return r;
 }
 
+// ---- quantised four-wide record (Node4Q) -----------------------------------------------------------------------------------
+// From a Node4 of a compact_ok scene.  The decoded box of every child contains its binary32 box: lo steps are rounded down,
+// hi steps up, and both are checked against the decoded value.  Returns false when an axis cannot be expressed (never for
+// finite boxes of sane size); the scene then keeps walking Node4.
+WRT_HD bool tb_node4q(const Node4& n, Node4Q& q) {
+    double corner[3] = {INFINITY, INFINITY, INFINITY}, far_[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const float* lo[3] = {n.lox, n.loy, n.loz};
+    const float* hi[3] = {n.hix, n.hiy, n.hiz};
+    bool any = false;
+    for (int i = 0; i < 4; ++i) {
+        if (n.desc[i] == WRT_NONE) continue;
+        any = true;
+        for (int k = 0; k < 3; ++k) { corner[k] = fmin(corner[k], (double)lo[k][i]); far_[k] = fmax(far_[k], (double)hi[k][i]); }
+    }
+    q.exps = 0;
+    q._pad[0] = q._pad[1] = 0;
+    float o[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < 3; ++k) { q.qlo[k] = 0; q.qhi[k] = 0; }
+    for (int k = 0; k < 3 && any; ++k) {
+        if (!(far_[k] >= corner[k]) || !(fabs(corner[k]) < 1e30) || !(fabs(far_[k]) < 1e30)) return false;
+        o[k] = (float)corner[k];  // exact: the corner is one of the binary32 lo values
+        int e = 0;
+        const double ext = far_[k] - corner[k];
+        if (ext > 0.0) { (void)frexp(ext / 255.0, &e); }  // ext / 255 = m * 2^e, m in [0.5, 1): step 2^e >= ext / 255
+        else e = -120;
+        if (e < -120) e = -120;
+        for (;;) {
+            if (e + 127 > 254) return false;
+            const double step = ldexp(1.0, e);
+            bool ok = true;
+            uint32_t wlo = 0, whi = 0;
+            for (int i = 0; i < 4 && ok; ++i) {
+                if (n.desc[i] == WRT_NONE) { wlo |= 255u << (8 * i); continue; }  // empty slot: inverted (lo 255, hi 0)
+                double a = floor(((double)lo[k][i] - corner[k]) / step);
+                if (corner[k] + a * step > (double)lo[k][i]) a -= 1.0;
+                if (a < 0.0) a = 0.0;  // (the corner itself: decoded == lo)
+                double b = ceil(((double)hi[k][i] - corner[k]) / step);
+                if (corner[k] + b * step < (double)hi[k][i]) b += 1.0;
+                if (b > 255.0 || a > 255.0) { ok = false; break; }
+                wlo |= (uint32_t)a << (8 * i);
+                whi |= (uint32_t)b << (8 * i);
+            }
+            if (ok) { q.qlo[k] = wlo; q.qhi[k] = whi; q.exps |= (uint32_t)(e + 127) << (8 * k); break; }
+            ++e;
+        }
+    }
+    q.ox = o[0]; q.oy = o[1]; q.oz = o[2];
+    for (int i = 0; i < 4; ++i) {
+        if (n.desc[i] == WRT_NONE) q.word[i] = WRT_NONE;
+        else if (n.desc[i] & 0x80000000u) q.word[i] = n.desc[i];
+        else q.word[i] = n.end[i] & 0x7FFFFFFFu;  // single-primitive leaf (compact_ok): kind + record index
+    }
+    return true;
+}
+
 }  // namespace wrt
