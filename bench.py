@@ -276,7 +276,10 @@ def measure_workload(wrt, host, ctx, key, spp_override, seed, steps, warmup):
     imgs, _ = scene_images(wl["scene"])
     scene = host.HostScene(wl["scene"], seed=1, synthetic_prims=wl.get("n_prims", 0), images=imgs)
     ctx.upload_scene(scene.flat())
+    up_first_ms = ctx.stats().upload_ms  # first upload of a scene of this size on this context: pays the driver's first mapping of the buffers
+    ctx.upload_scene(scene.flat())
     up_ms = ctx.stats().upload_ms
+    tree_ms, tree_dev = ctx.stats().tree_build_ms, ctx.stats().tree_build_device
     W, H = wl["width"], wl["height"]
     cam = scene.camera(W, H)
     params = scene.params(W, H, spp, wl["depth"], seed=seed, cull_mode=wrt.WRT_CULL_AUTO)
@@ -291,7 +294,9 @@ def measure_workload(wrt, host, ctx, key, spp_override, seed, steps, warmup):
     hbm_peak, _ = measured_peaks()
     rec = {"workload": wl["name"], "spp": spp, "reduced_spp": spp != wl["spp"], "steps": steps, "warmup": warmup,
            "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps, "rays_per_step": rays / steps,
-           "upload_ms": up_ms, "traversal": "packet" if ctx.stats().program_ops <= 96 else "ordered, per lane",
+           "upload_ms": up_ms, "upload_ms_first": up_first_ms, "tree_build_ms": tree_ms, "tree_build_on_device": bool(tree_dev), "traversal": ("packet" if ctx.stats().program_ops <= 96 else
+                         ("wavefront, persistent per-lane extend over four-wide records" if ctx.stats().n_tree_records >= 16384 and tree_dev
+                          else "ordered, per lane")),
            "roofline_hbm_frac": (rays / (kms * 1e-3)) * wl["b_ray"] / 1e9 / hbm_peak,
            "algorithmic_bytes_per_ray": wl["b_ray"], "algorithmic_fp64_instr_per_ray": wl["f_ray"]}
     scene.close() if hasattr(scene, "close") else None
@@ -474,7 +479,7 @@ def main():
                      "traffic": (wl["dram_b_per_ray_ncu"] * rays_all / args.steps / n_gpus) if "dram_b_per_ray_ncu" in wl else None,
                      "traffic_unit": "bytes per launch (ncu DRAM bytes per ray x rays of this launch; source in profiles/README.md)",
                      "algorithmic_bytes_per_launch": wl["b_ray"] * rays_all / args.steps / n_gpus,
-                     "kernel": ("wavefront iteration loop (wf_extend_ordered_kernel = 84 % of its GPU time, profiles/README.md)"
+                     "kernel": ("wavefront iteration loop (wf_extend_ordered_kernel = 81 % of its GPU time, profiles/README.md)"
                                 if launches_all / args.steps / n_gpus > 16 else "render_kernel"),
                      "kernel_ms_per_launch": kern_ms_max / args.steps,
                      "algorithmic_bytes_per_ray": wl["b_ray"], "peak_source": peak_src,

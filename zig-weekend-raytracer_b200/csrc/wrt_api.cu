@@ -283,8 +283,17 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     if (rc) return rc;
     ctx->have_scene = false;
     ctx->last_valid = false;
+    const bool trace = std::getenv("WRT_TRACE_BUILD") != nullptr;
+    auto t_last = t0;
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "wrt trace: upload: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     rc = upload_images(ctx, scene);
     if (rc != WRT_OK) return rc;
+    lap("images");
     CU(ctx->d_ops.upload(cs.ops, ctx->stream));
     if (!cs.ops_pruned.empty()) CU(ctx->d_ops_pruned.upload(cs.ops_pruned, ctx->stream));
     CU(ctx->d_boxes_ref.upload(cs.boxes_ref, ctx->stream));
@@ -304,7 +313,9 @@ int wrt::upload_compiled(wrt_ctx* ctx, const wrt::CompiledScene& cs, const wrt_s
     CU(ctx->d_textures.upload(cs.textures, ctx->stream));
     CU(ctx->d_lights.upload(cs.lights, ctx->stream));
     CU(ctx->d_light_boxes.upload(cs.light_boxes, ctx->stream));
+    lap("buffers sized, copies queued");
     CU(cudaStreamSynchronize(ctx->stream));
+    lap("copies done");
     wrt::DeviceScene& ds = ctx->ds;
     ds.ops = ctx->d_ops.p; ds.boxes_ref = ctx->d_boxes_ref.p; ds.boxes_tight = ctx->d_boxes_tight.p; ds.nodes2 = ctx->d_nodes2.p; ds.nodes4 = ctx->d_nodes4.p; ds.root4 = ctx->d_root4.p;
     ds.spheres = ctx->d_spheres.p; ds.sphere_aux = ctx->d_sphere_aux.p; ds.quads = ctx->d_quads.p;
