@@ -582,3 +582,36 @@ def test_cli_renders_a_ppm(wrt, wro, tmp_path):
     diff = sum(1 for x, y in zip(got.split(b"\n"), body.split(b"\n")) if x != y)
     assert diff <= 3
     sc.close()
+
+
+def test_compact_entries_and_quantised_records_change_no_bit(wrt, wro):
+    """The wavefront's extend kernel on a flat one-tree scene walks quantised 64-byte records with 8-byte stack entries
+    (wrt_device.cuh: Node4Q, TravCompactStack).  Neither may move a bit of the frame: the per-lane megakernel (binary32
+    four-wide records, 16-byte entries) and the same engine with each form switched off are the comparison."""
+    import os
+    sc = wro.OracleScene("synthetic", seed=4, n_prims=40000)
+    flat = sc.flatten()
+    info = wrt.check_scene(flat)
+    assert info.compact_stack == 1 and info.quantised_records > 0
+    w, h = 128, 72
+    cam = sc.camera(w, h)
+    chunks = wrt.WRT_FLAG_CHUNKS(2)
+    frames, rays = {}, {}
+    for label, env, engine in (("megakernel", {}, wrt.WRT_FLAG_ENGINE_MEGAKERNEL),
+                               ("wavefront, compact + quantised", {}, wrt.WRT_FLAG_ENGINE_WAVEFRONT),
+                               ("wavefront, compact, binary32 records", {"WRT_QUANT_RECORDS": "0"}, wrt.WRT_FLAG_ENGINE_WAVEFRONT),
+                               ("wavefront, 16-byte entries", {"WRT_COMPACT_STACK": "0"}, wrt.WRT_FLAG_ENGINE_WAVEFRONT)):
+        os.environ.update(env)
+        try:
+            with wrt.Context(0) as c:   # the forms are chosen at upload
+                c.upload_scene(flat)
+                frames[label] = c.render(cam, sc.params(w, h, 16, 20, seed=9, flags=engine | chunks)).copy()
+                rays[label] = (c.stats().rays, c.stats().paths)
+        finally:
+            for k in env:
+                del os.environ[k]
+    ref = frames["megakernel"]
+    for label, f in frames.items():
+        np.testing.assert_array_equal(ref.view(np.uint64), f.view(np.uint64), err_msg=label)
+        assert rays[label] == rays["megakernel"], label
+    sc.close()

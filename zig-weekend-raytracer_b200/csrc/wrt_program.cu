@@ -184,6 +184,7 @@ struct Compiler {
 
     // ---- program emission ------------------------------------------------------------------------------
     uint32_t nest = 0;  // current nesting of bvh_node / instance ops (bounds the ordered traversal's stack)
+    const bool keep_ref_records = keep_reference_trees();
     std::vector<TreeItem>* cur_items = nullptr;  // != null while emitting below a bvh_node; out.tree_inputs collects every reference BVH
     bool emit(uint32_t id, uint32_t xf, uint32_t xf_depth) {
         if (!check_entity(id, "emit")) return false;
@@ -258,7 +259,10 @@ struct Compiler {
                     cur_items = nullptr;
                     if (ok) out.tree_inputs.push_back(TreeInput{box, nest, std::move(root_items)});
                 }
-                if (ok) {  // child-pair record for the ordered traversal: both children's boxes + where they live in the program
+                // child-pair record of the reference topology: both children's boxes + where they live in the program.  Only the
+                // records the ordered traversal can reach are formed: every root's (a tree of fewer than two leaves is not
+                // rebuilt), and all of them when WRT_REFERENCE_TREE=1 keeps the reference topology.
+                if (ok && (is_root || keep_ref_records)) {
                     Node2 n2;
                     Box3 lb, rb;
                     lb.reset(); rb.reset();
