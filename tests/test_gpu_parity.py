@@ -615,3 +615,29 @@ def test_compact_entries_and_quantised_records_change_no_bit(wrt, wro):
         np.testing.assert_array_equal(ref.view(np.uint64), f.view(np.uint64), err_msg=label)
         assert rays[label] == rays["megakernel"], label
     sc.close()
+
+
+def test_lean_extend_state_on_an_instanced_scene(wrt, wro, images):
+    """The persistent extend kernel keeps no binary64 ray in its traversal state (TravLean): leaf ops, transform pushes / pops
+    and pops across transform contexts re-form it from the world ray of the path record.  rtw_final has translated and rotated
+    instances with a nested tree; forced onto four-wide records and the wavefront engine it must give the megakernel's frame."""
+    import os
+    sc = wro.OracleScene("rtw_final", seed=1, images=images)
+    w, h = 96, 96
+    cam = sc.camera(w, h)
+    chunks = wrt.WRT_FLAG_CHUNKS(2)
+    frames = {}
+    for wide in ("0", "1"):
+        os.environ["WRT_WIDE_TREE"] = wide
+        try:
+            with wrt.Context(0) as c:
+                c.upload_scene(sc.flatten())
+                for engine in (wrt.WRT_FLAG_ENGINE_MEGAKERNEL, wrt.WRT_FLAG_ENGINE_WAVEFRONT):
+                    p = sc.params(w, h, 8, 20, seed=3, cull_mode=wrt.WRT_CULL_TIGHT, flags=engine | chunks)
+                    frames[(wide, engine)] = c.render(cam, p).copy()
+        finally:
+            del os.environ["WRT_WIDE_TREE"]
+    ref = frames[("0", wrt.WRT_FLAG_ENGINE_MEGAKERNEL)]
+    for key, f in frames.items():
+        np.testing.assert_array_equal(ref.view(np.uint64), f.view(np.uint64), err_msg=str(key))
+    sc.close()
