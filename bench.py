@@ -67,6 +67,7 @@ def parse_args():
                     help="minute-long frames: time each step ONCE — the e2e call (upload + render into host memory) — and take "
                          "`value` from the device events of that same render instead of rendering every frame twice")
     ap.add_argument("--engine", default="auto", choices=["auto", "megakernel", "wavefront"], help="development: force an engine")
+    ap.add_argument("--chunks", type=int, default=0, help="development: pin the sample-chunk count (WRT_FLAG_CHUNKS); 0 = the library's rule")
     ap.add_argument("--shard", default="rows", choices=["rows", "samples"], help="N > 1: what the devices split")
     ap.add_argument("--no-all-workloads", dest="all_workloads", action="store_false",
                     help="skip the short runs of the other BASELINE configs after the headline timing")
@@ -336,6 +337,8 @@ def main():
     cull = {"auto": wrt.WRT_CULL_AUTO, "tight": wrt.WRT_CULL_TIGHT, "reference": wrt.WRT_CULL_REFERENCE}[args.cull]
     flags = wrt.WRT_FLAG_SHARD_SAMPLES if args.shard == "samples" else 0
     flags |= {"auto": 0, "megakernel": wrt.WRT_FLAG_ENGINE_MEGAKERNEL, "wavefront": wrt.WRT_FLAG_ENGINE_WAVEFRONT}[args.engine]
+    if args.chunks:
+        flags |= wrt.WRT_FLAG_CHUNKS(args.chunks)
     imgs, img_note = scene_images(wl["scene"])
     scene = host.HostScene(wl["scene"], seed=1, synthetic_prims=wl.get("n_prims", 0), images=imgs)
     flat = scene.flat()
@@ -459,7 +462,7 @@ def main():
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "spp": spp, "depth": depth,
-                   "engine": args.engine, "cull": args.cull + (" -> " + ("reference" if stats0.cull_mode_used == wrt.WRT_CULL_REFERENCE else "tight")),
+                   "engine": args.engine, "sample_chunks": (args.chunks or "library rule"), "cull": args.cull + (" -> " + ("reference" if stats0.cull_mode_used == wrt.WRT_CULL_REFERENCE else "tight")),
                    "parallelism": (f"{'sample-range' if args.shard == 'samples' else 'row-interleaved'} shards x{n_gpus}"
                                    + (" + NCCL gather inside wrt_render_sharded" if n_gpus > 1 else "")),
                    "l2_policy": "scene is cache-resident by design; per-step traffic is the framebuffer (> L2 only for C5)",
