@@ -482,9 +482,15 @@ struct Freer {  // frees what was allocated when the build leaves, on every path
 bool want_device_build(const CompiledScene& cs) {
     const char* env = std::getenv("WRT_DEVICE_BUILD");
     if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
-    size_t items = 0;
-    for (const TreeInput& r : cs.tree_inputs) items += r.items.size();
-    return items >= 32768;  // below that the host build takes a few milliseconds and the launches of ~20 levels cost as much
+    // The device build runs one tree after the other, ~10 launches and one host synchronisation per level: it pays for a big
+    // tree (below 32 768 leaves the host build takes a few milliseconds and ~20 levels of launches cost as much), not for a
+    // scene that is a crowd of small ones.
+    size_t largest = 0, n_trees = 0;
+    for (const TreeInput& r : cs.tree_inputs) {
+        largest = std::max(largest, r.items.size());
+        n_trees += r.items.size() >= 2 ? 1 : 0;
+    }
+    return largest >= 32768 && n_trees <= 64;
 }
 
 #define BCU(call)                                                                                   \
