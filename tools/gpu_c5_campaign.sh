@@ -1,6 +1,6 @@
 #!/bin/bash
 # BASELINE.json configs[4] as stated: 2^20 primitives, 3840x2160, 1 024 spp, depth 20, on N GPUs of this box.
-# usage: tools/gpu_r02_c5_campaign.sh N   (N = 1 launches plain python, N > 1 torchrun; one timed frame, fused e2e timing)
+# usage: tools/gpu_c5_campaign.sh N   (N = 1 launches plain python, N > 1 torchrun; one timed frame, fused e2e timing)
 set -u
 N=${1:-1}
 mkdir -p gpurun_out

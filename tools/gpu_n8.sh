@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-bash tools/gpu_r02_c5_campaign.sh 8
+bash tools/gpu_c5_campaign.sh 8
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r02_scale_c2_n8.json 2> gpurun_out/r02_scale_c2_n8.err; echo "c2 n8 rc=$?"
 python - <<'P'
 import json

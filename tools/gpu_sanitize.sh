@@ -1,5 +1,5 @@
 #!/bin/bash
-# compute-sanitizer on small renders through the CLI (one tool per gpurun call): usage tools/gpu_r02_sanitize.sh memcheck|racecheck
+# compute-sanitizer on small renders through the CLI (one tool per gpurun call): usage tools/gpu_sanitize.sh memcheck|racecheck
 set -u
 TOOL=${1:-memcheck}
 mkdir -p gpurun_out
