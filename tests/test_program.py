@@ -100,3 +100,26 @@ def test_compact_form_is_offered_only_to_flat_single_tree_scenes(wrt, wro, image
         info = wrt.check_scene(sc.flatten())
         assert info.compact_stack == 0 and info.quantised_records == 0
         sc.close()
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1.0, 3e7])
+def test_quantised_records_stay_conservative_at_any_scene_scale(wrt, wro, scale):
+    """Node4Q boxes are 8-bit offsets from the record's corner with a power-of-two step per axis: whatever the magnitude of
+    the coordinates, the decoded box must contain the binary32 box and be less than one step loose (wrt_check_scene verifies
+    every record), and the tree must still reach every primitive once."""
+    sc = wro.OracleScene("synthetic", seed=7, n_prims=20000)
+    flat = sc.flatten()
+    for i in range(flat.n_spheres):
+        s = flat.spheres[i]
+        for k in range(3):
+            s.center[k] *= scale
+        s.radius *= scale
+    for i in range(flat.n_quads):
+        q = flat.quads[i]
+        for k in range(3):
+            q.start[k] *= scale
+            q.u[k] *= scale
+            q.v[k] *= scale
+    info = wrt.check_scene(flat)
+    assert info.compact_stack == 1 and info.quantised_records == info.n_tree_records
+    sc.close()
