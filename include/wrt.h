@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WRT_ABI_VERSION 2u
+#define WRT_ABI_VERSION 3u  /* 3: wrt_stats and wrt_scene_info grew at the tail, wrt_build_trees added (round 2) */
 #define WRT_NONE 0xFFFFFFFFu
 
 /* status codes */

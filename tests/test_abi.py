@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(wrt):
     lib = C.CDLL(str(wrt.LIB_PATH))
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} is declared in include/wrt.h but not exported by libwrt.so"
-    assert lib.wrt_abi_version() == 2
+    assert lib.wrt_abi_version() == 3
 
 
 def test_library_exports_nothing_else(wrt):
@@ -82,7 +82,7 @@ def test_ctypes_mirror_matches_c_layout(wrt, tmp_path):
 
 def test_header_is_plain_c(tmp_path):
     src = tmp_path / "c89ish.c"
-    src.write_text(f'#include "{HEADER}"\nint main(void) {{ return (int)WRT_ABI_VERSION - 2; }}\n')
+    src.write_text(f'#include "{HEADER}"\nint main(void) {{ return (int)WRT_ABI_VERSION - 3; }}\n')
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-o", str(tmp_path / "a.out"), str(src)])
 
 

@@ -53,7 +53,7 @@ def test_host_built_scene_equals_oracle_built_scene(host, wro, images, name, w, 
 def test_flat_scene_is_well_formed(host, images):
     hs = host.HostScene("rtw_final", seed=1, images=images)
     f = hs.flat()
-    assert f.abi_version == 2 and f.root < f.n_entities and f.lights < f.n_entities
+    assert f.abi_version == 3 and f.root < f.n_entities and f.lights < f.n_entities
     kinds = [f.entities[i].kind for i in range(f.n_entities)]
     assert kinds.count(4) == 1 and kinds.count(5) == 1            # one Translate(RotateY(...))
     assert kinds.count(3) == 7 + 1023 + 511                        # BVH node counts

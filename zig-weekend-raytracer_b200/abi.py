@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-WRT_ABI_VERSION = 2
+WRT_ABI_VERSION = 3
 WRT_NONE = 0xFFFFFFFF
 WRT_CULL_AUTO = 0       # default: TIGHT when every reference box contains its subtree, else REFERENCE
 WRT_CULL_REFERENCE = 1
